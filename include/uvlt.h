@@ -1,0 +1,167 @@
+/*
+ * uvlt.h -- C ABI of libuvlt_sm100.so, the B200 (sm_100a) implementation of UVLTrack's per-frame forward hot path.
+ *
+ * The reference (OpenSpaceAI/UVLTrack) is pure Python/PyTorch: it has no FFI of its own.  The entry points below
+ * are what a reference-side binding for this path binds (ctypes stub shown in INTEGRATION.md); each one cites the
+ * reference function it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C, no torch types: raw device pointers, sizes, an opaque handle and a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on failure; uvlt_last_error() returns a thread-local message.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - all work is enqueued on the caller's stream; no hidden synchronisation unless documented.
+ *   - caller owns every tensor it passes in; the library owns only its packed weights and workspace arenas.
+ *   - a handle is bound to one device and is not thread-safe (one process per GPU, as the reference's
+ *     lib/test/evaluation/running.py:97-100 does).
+ */
+#ifndef UVLT_H_
+#define UVLT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVLT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define UVLT_API __attribute__((visibility("default")))
+#else
+#define UVLT_API
+#endif
+
+/* activation codes for the GEMM epilogue */
+#define UVLT_ACT_NONE 0
+#define UVLT_ACT_GELU 1 /* exact erf GELU: lib/models/backbones/utils.py:50, bert_backbone.py:118-124 */
+#define UVLT_ACT_RELU 2 /* lib/models/heads/utils.py:126-130 */
+
+UVLT_API int uvlt_abi_version(void);
+UVLT_API const char* uvlt_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine: the whole per-frame path behind UVLTrack.forward_test (lib/models/uvltrack/uvltrack.py:41-45)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct uvlt_engine* uvlt_handle;
+
+typedef struct uvlt_config {
+  int32_t embed_dim;       /* cfg.MODEL.HIDDEN_DIM: 768 (B) / 1024 (L) */
+  int32_t num_heads;       /* 12 / 16 (head dim is 64 for both, mae_vit.py:218-229) */
+  int32_t depth;           /* 12 / 24 transformer blocks */
+  int32_t mlp_hidden;      /* 4 * embed_dim */
+  int32_t template_size;   /* cfg.DATA.TEMPLATE.SIZE (pixels, multiple of 16) */
+  int32_t search_size;     /* cfg.DATA.SEARCH.SIZE */
+  int32_t text_len;        /* cfg.MODEL.BACKBONE.LANGUAGE.BERT.MAX_QUERY_LEN (40) */
+  int32_t fusion_start;    /* min(cfg.MODEL.BACKBONE.FUSION_LAYER); layers >= this run jointly over image+text */
+  int32_t head_channels;   /* cfg.MODEL.HEAD.HEAD_DIM (256) */
+  int32_t vocab_size;      /* BERT vocabulary (30522) */
+  int32_t max_position;    /* BERT max_position_embeddings (512) */
+  int32_t max_batch;       /* largest number of sequences per call */
+  int32_t softmax_one;     /* cfg.MODEL.HEAD.SOFTMAX_ONE */
+  int32_t offset_sigmoid;  /* cfg.MODEL.HEAD.OFFSET_SIGMOID */
+  int32_t txt_token_mean;  /* cfg.MODEL.BACKBONE.TXT_TOKEN_MODE == 'mean' (0 = 'cls') */
+  int32_t num_cont_layers; /* len(cfg.MODEL.BACKBONE.CONT_LOSS_LAYER) */
+  int32_t cont_layers[32]; /* cfg.MODEL.BACKBONE.CONT_LOSS_LAYER */
+} uvlt_config;
+
+/* Replaces build_model(cfg) (lib/models/uvltrack/uvltrack.py:47-57): allocates weight + workspace arenas. */
+UVLT_API int uvlt_create(const uvlt_config* cfg, uvlt_handle* out);
+UVLT_API void uvlt_destroy(uvlt_handle h);
+
+/* Replaces nn.Module.load_state_dict (lib/test/tracker/uvltrack.py:24).  `key` is the reference state_dict key
+ * (e.g. "backbone.vit.blocks.3.attn.qkv.weight"); `data` is a HOST pointer to contiguous fp32.  Unknown keys are
+ * ignored and reported through the return value 2 (strict=False semantics).  */
+UVLT_API int uvlt_set_weight(uvlt_handle h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+/* Repack: fp32 -> bf16 GEMM operands, fused BERT q/k/v, conv weights to (ky,kx,c) order with BatchNorm folded
+ * (lib/models/heads/utils.py:126-130).  Fails if a required tensor was never set.  Synchronises the device. */
+UVLT_API int uvlt_finalize_weights(uvlt_handle h);
+
+typedef struct uvlt_outputs {
+  /* all device pointers into the engine's arena, valid until the next forward on this handle; fp32 */
+  const float* tokens;        /* [B, 1+Nz+Nx+T, D] final token stream: rows [cls | template | search | text] */
+  const float* cls_score;     /* [B, S, S]   'cls_score' == 'cls_score_test' (JOINT_CLS false) */
+  const float* bbox_map;      /* [B, S*S, 4] (cx, cy, w, h) relative to the search crop */
+  const float* pred_boxes;    /* [B, 4]      bbox_map at argmax(cls * softmax(cont)[..., 0]) */
+  const float* cont_score;    /* [B, S*S, 3] (2 when softmax_one == 0) */
+  const float* cont_prob;     /* [B, S*S]    softmax(cont_score)[..., 0] */
+  const float* logits;        /* [B, num_cont_layers, S, S] backbone contrastive logits (0 when disabled) */
+  int32_t batch, n_tokens, embed_dim, feat_size;
+} uvlt_outputs;
+
+/* UVLTrack.forward_test (lib/models/uvltrack/uvltrack.py:41-45).
+ *   template [B,3,Hz,Hz] fp32, search [B,3,Hx,Hx] fp32, ids int64 [B,T], text_mask fp32 [B,T] (1 = real token),
+ *   prompt fp32 [B,3,D], flag int64 [B] (0 BBOX, 1 NL, 2 NL+BBOX) -- all DEVICE pointers. */
+UVLT_API int uvlt_forward_test(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
+                      const float* text_mask, const float* prompt, const int64_t* flag, int32_t batch,
+                      int32_t want_logits, uvlt_outputs* out, void* stream);
+
+/* Backbone only + prompter: UVLTrack.forward_prompt_init / forward_prompt
+ * (lib/models/uvltrack/uvltrack.py:26-38, lib/models/heads/utils.py:78-99).  Uses the token stream of the LAST
+ * forward on this handle when run_backbone == 0 (forward_prompt semantics: out_dict of an earlier forward_test).
+ *   template_mask uint8 [B,Nz], context_mask uint8 [B,Nx] (1 = inside the target box), prompt_out fp32 [B,3,D]. */
+UVLT_API int uvlt_forward_prompt(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
+                        const float* text_mask, const int64_t* flag, const uint8_t* template_mask,
+                        const uint8_t* context_mask, int32_t batch, int32_t run_backbone, float* prompt_out,
+                        void* stream);
+
+/* Post-processing of Tracker.track (lib/test/tracker/uvltrack.py:116-121): merge = cls * window * softmax(cont)[0]
+ * in float64, argmax, gather.  window: device float64 [S*S].  out: device fp32 [B,6] = cx,cy,w,h,score,index. */
+UVLT_API int uvlt_track_decode(uvlt_handle h, const double* window, int32_t has_cont, float* out, void* stream);
+
+/* Same path end to end with HOST buffers (pinned recommended): copies the inputs to the device, runs
+ * forward_test + track decode, copies [B,6] results back and synchronises the stream.  This is the call the
+ * bench's e2e number is measured through. */
+UVLT_API int uvlt_track_frame_host(uvlt_handle h, const float* tmpl_host, const float* search_host, const int64_t* ids_host,
+                          const float* text_mask_host, const float* prompt_host, const int64_t* flag_host,
+                          const double* window_dev, int32_t batch, int32_t update_template, float* out_host,
+                          void* stream);
+
+/* number of kernels the last forward launched (for bench.py's gpu_launches) */
+UVLT_API int uvlt_last_launch_count(uvlt_handle h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator-level entry points (device pointers; used by the per-operator parity tests)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + resid;  A, W bf16 row-major; bias fp32 [N] or NULL; resid fp32 [M,N]
+ * or NULL (may alias out when out_f32); out bf16 or fp32.  nn.Linear semantics (block.py:49,59; utils.py:63-69).
+ * bn: tile width 32/64/128, 0 = auto.  Requires K % 64 == 0, N % 32 == 0. */
+UVLT_API int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* resid, void* out, int M, int N, int K,
+                 int act, int out_f32, int bn, void* stream);
+
+/* groups independent GEMMs (the four conv towers): A [G][M,K], W [G][N,K], bias [G][N],
+ * out bf16 at out + g*out_gstride + row*out_ld. */
+UVLT_API int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,
+                         int act, long long out_ld, long long out_gstride, int bn, void* stream);
+
+/* Fused MHA on packed qkv bf16 [B, n, 3*H*64] -> out bf16 [B, n, H*64]; key_bias fp32 [B, n] or NULL.
+ * (block.py:47-58, bert_backbone.py:299-325).  v_t != NULL selects the bring-up variant with V^T [B,H*64,n_pad]. */
+UVLT_API int uvlt_op_attention(const void* qkv, const float* key_bias, void* out, int B, int n, int H, const void* v_t,
+                      int n_pad, void* stream);
+
+/* LayerNorm over rows gathered from two fp32 streams (see csrc/rowwise.cuh LnParams). */
+UVLT_API int uvlt_op_layernorm(const float* src0, int rows0, const float* src1, int rows1, const float* add0,
+                      const float* add1, int split, float* dst_f32, int dst_mode, void* dst_bf16, const float* gamma,
+                      const float* beta, float eps, int B, int D, void* stream);
+
+/* mae_vit.py:92,99,203-214: patchify as im2col (bf16 [B*(Nz+Nx), 768]) + cls rows of the token stream. */
+UVLT_API int uvlt_op_patch_im2col(const float* tmpl, const float* srch, int B, int Hz, int Hx, void* out, const float* cls,
+                         float* x_stream, int D, void* stream);
+
+/* 3x3/pad-1 im2col on an SxS token grid, G channel groups of C channels -> bf16 [G][B*S*S][9*C] (ky,kx,c). */
+UVLT_API int uvlt_op_im2col3x3(const void* src, int src_f32, long long src_bstride, long long src_row_off, long long src_ld,
+                      int G, int C, int S, int B, void* dst, void* stream);
+
+/* bert_backbone.py:260-274 */
+UVLT_API int uvlt_op_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0,
+                       const float* gamma, const float* beta, float* dst_f32, void* dst_bf16, int B, int T, int D,
+                       int vocab, void* stream);
+
+/* modality_unified_feature_extractor.py:43-50 + bert_backbone.py:746-748 as additive key biases. */
+UVLT_API int uvlt_op_build_bias(const long long* flag, const float* text_mask, int B, int Nz, int Nx, int T, float* bias_vis,
+                       float* bias_joint, float* bias_bert, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVLT_H_ */

@@ -1,0 +1,247 @@
+// Box-head tail kernels: final 1x1 convs + sigmoid, contrastive-alignment similarity,
+// softmax-one, score map, box decode, and the Hanning-windowed argmax of Tracker.track().
+// All HBM-bound / latency-bound: one warp per search token, warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace uvlt {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ----------------------------------------------------------------------------------------------
+// modality_adaptive_box_head.py:73-82 (last Conv2d(32->{1,2,2,2}, k=1) + sigmoid, size tower chosen by flag),
+// :140-148 (cont_score = e^{logit_scale} * <x^, p^_k>, softmax-one), :108-119 (ctr = (grid + offset) / S, bbox_map)
+// ----------------------------------------------------------------------------------------------
+struct HeadFinalParams {
+  const __nv_bfloat16* y4;  // [B*SS, 4*C4]  tower order: cls | offset | size(track) | size(grounding)
+  int C4;                   // channels of the last 3x3 layer (HEAD_DIM / 8 = 32)
+  const float* w5;          // [7, C4]  rows: cls, off_x, off_y, w_tr, h_tr, w_gr, h_gr
+  const float* b5;          // [7]
+  const float* x_stream;    // fp32 token stream [B, n_tok, D]
+  long long x_bstride;      // n_tok * D
+  int x_row_off;            // first search token row (1 + Nz)
+  int D;
+  const float* prompt;      // [B, 3, D]
+  const long long* flag;    // [B]
+  float logit_scale_exp;
+  int softmax_one;
+  int offset_sigmoid;
+  int S, B;
+  float* cls_map;           // [B, SS]
+  float* bbox_map;          // [B, SS, 4]  (cx, cy, w, h) relative to the search crop
+  float* cont_score;        // [B, SS, 3] (softmax_one) or [B, SS, 2]
+  float* cont_prob;         // [B, SS]  softmax(cont_score)[..., 0]
+};
+
+__global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SS = p.S * p.S;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= p.B * SS) return;
+  const int b = r / SS, t = r - b * SS;
+  const long long f = p.flag[b];
+
+  // ---- last 1x1 convs: 7 dot products of length C4 over the four tower outputs ----
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* y = p.y4 + static_cast<long long>(r) * 4 * p.C4;
+  for (int c = lane; c < p.C4; c += 32) {
+    const float y_cls = __bfloat162float(y[c]);
+    const float y_off = __bfloat162float(y[p.C4 + c]);
+    const float y_tr = __bfloat162float(y[2 * p.C4 + c]);
+    const float y_gr = __bfloat162float(y[3 * p.C4 + c]);
+    acc[0] += y_cls * p.w5[c];
+    acc[1] += y_off * p.w5[p.C4 + c];
+    acc[2] += y_off * p.w5[2 * p.C4 + c];
+    acc[3] += y_tr * p.w5[3 * p.C4 + c];
+    acc[4] += y_tr * p.w5[4 * p.C4 + c];
+    acc[5] += y_gr * p.w5[5 * p.C4 + c];
+    acc[6] += y_gr * p.w5[6 * p.C4 + c];
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]) + p.b5[i];
+  const float cls = sigmoidf_(acc[0]);
+  const float off_x = p.offset_sigmoid ? sigmoidf_(acc[1]) : acc[1];
+  const float off_y = p.offset_sigmoid ? sigmoidf_(acc[2]) : acc[2];
+  const bool gr = (f == 1);  // size_map_group = [track, grounding, track][flag]
+  const float bw = sigmoidf_(gr ? acc[5] : acc[3]);
+  const float bh = sigmoidf_(gr ? acc[6] : acc[4]);
+
+  // ---- contrastive alignment: L2-normalised search token vs the three prompts ----
+  const float* x = p.x_stream + static_cast<long long>(b) * p.x_bstride + static_cast<long long>(p.x_row_off + t) * p.D;
+  const float* pr = p.prompt + static_cast<long long>(b) * 3 * p.D;
+  float xx = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  for (int i = lane * 4; i < p.D; i += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(pr + i));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(pr + p.D + i));
+    const float4 e = __ldg(reinterpret_cast<const float4*>(pr + 2 * p.D + i));
+    xx += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+    d0 += xv.x * a.x + xv.y * a.y + xv.z * a.z + xv.w * a.w;
+    d1 += xv.x * c.x + xv.y * c.y + xv.z * c.z + xv.w * c.w;
+    d2 += xv.x * e.x + xv.y * e.y + xv.z * e.z + xv.w * e.w;
+    n0 += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    n1 += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+    n2 += e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w;
+  }
+  xx = warp_sum(xx); d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+  n0 = warp_sum(n0); n1 = warp_sum(n1); n2 = warp_sum(n2);
+  const float inv_x = 1.0f / fmaxf(sqrtf(xx), 1e-12f);  // F.normalize: v / max(||v||, eps)
+  const float c0 = p.logit_scale_exp * d0 * inv_x / fmaxf(sqrtf(n0), 1e-12f);
+  const float c1 = p.logit_scale_exp * d1 * inv_x / fmaxf(sqrtf(n1), 1e-12f);
+  const float c2 = p.logit_scale_exp * d2 * inv_x / fmaxf(sqrtf(n2), 1e-12f);
+  float s1, prob0;
+  if (p.softmax_one) {
+    s1 = fmaxf(fmaxf(c1, c2), 0.0f);
+    const float m = fmaxf(fmaxf(c0, s1), 0.0f);
+    const float e0 = expf(c0 - m), e1 = expf(s1 - m), e2 = expf(0.0f - m);
+    prob0 = e0 / (e0 + e1 + e2);
+  } else {
+    s1 = fmaxf(c1, c2);
+    const float m = fmaxf(c0, s1);
+    const float e0 = expf(c0 - m), e1 = expf(s1 - m);
+    prob0 = e0 / (e0 + e1);
+  }
+  if (lane == 0) {
+    p.cls_map[r] = cls;
+    const int col = t % p.S, row = t / p.S;  // coodinate channel 0 = column index (cx), channel 1 = row index (cy)
+    const float add = p.offset_sigmoid ? 0.0f : 0.5f;
+    float4 bb;
+    bb.x = (static_cast<float>(col) + add + off_x) / static_cast<float>(p.S);
+    bb.y = (static_cast<float>(row) + add + off_y) / static_cast<float>(p.S);
+    bb.z = bw;
+    bb.w = bh;
+    *reinterpret_cast<float4*>(p.bbox_map + static_cast<long long>(r) * 4) = bb;
+    if (p.softmax_one) {
+      float* cs = p.cont_score + static_cast<long long>(r) * 3;
+      cs[0] = c0; cs[1] = s1; cs[2] = 0.0f;
+    } else {
+      float* cs = p.cont_score + static_cast<long long>(r) * 2;
+      cs[0] = c0; cs[1] = s1;
+    }
+    p.cont_prob[r] = prob0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Per-sequence argmax + gather.  One CTA per sequence, first-max tie rule (torch.argmax).
+//   mode 0 (convert2bbox, modality_adaptive_box_head.py:110-118): score = cls * prob0 in fp32 -> pred_boxes [B,4]
+//   mode 1 (Tracker.track, lib/test/tracker/uvltrack.py:116-121): merge = cls * window * prob0 evaluated in float64
+//          exactly as the reference does on the host (float32 maps promoted by the float64 numpy window);
+//          result row = [cx, cy, w, h, score = cls*prob0 (fp32), argmax index]
+// ----------------------------------------------------------------------------------------------
+struct DecodeParams {
+  const float* cls_map;    // [B, SS]
+  const float* cont_prob;  // [B, SS] or nullptr (has_cont == false -> 1)
+  const float* bbox_map;   // [B, SS, 4]
+  const double* window;    // [SS] (mode 1)
+  int SS, mode;
+  float* out;              // mode 0: [B, 4]; mode 1: [B, 6]
+};
+
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
+  __shared__ double s_val[8];
+  __shared__ int s_idx[8];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double best = -1.0e300;
+  int best_i = 0x7fffffff;
+  for (int t = threadIdx.x; t < p.SS; t += blockDim.x) {
+    const float c = p.cls_map[b * p.SS + t];
+    const float q = p.cont_prob ? p.cont_prob[b * p.SS + t] : 1.0f;
+    double v;
+    if (p.mode == 0) v = static_cast<double>(c * q);
+    else v = (static_cast<double>(c) * p.window[t]) * static_cast<double>(q);
+    if (v > best) { best = v; best_i = t; }  // strided scan keeps the smallest index per thread on ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_i)) { best = s_val[w]; best_i = s_idx[w]; }
+    if (best_i == 0x7fffffff) best_i = 0;  // all-NaN guard
+    const float4 bb = *reinterpret_cast<const float4*>(p.bbox_map + (static_cast<long long>(b) * p.SS + best_i) * 4);
+    if (p.mode == 0) {
+      *reinterpret_cast<float4*>(p.out + b * 4) = bb;
+    } else {
+      float* o = p.out + b * 6;
+      o[0] = bb.x; o[1] = bb.y; o[2] = bb.z; o[3] = bb.w;
+      const float q = p.cont_prob ? p.cont_prob[b * p.SS + best_i] : 1.0f;
+      o[4] = p.cls_map[b * p.SS + best_i] * q;
+      o[5] = static_cast<float>(best_i);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Backbone contrastive logits (modality_unified_feature_extractor.py:85-93), one cont-loss layer per launch:
+//   logit[b, t] = e^{ls} * <x^_t, token^>  with token^ = vis / txt, and their average of the two logits for flag 2.
+// ----------------------------------------------------------------------------------------------
+struct BackboneLogitParams {
+  const float* img;        // token stream holding [cls | z | x] rows
+  long long img_bstride;   // elements between batch elements
+  const float* txt;        // text rows (txt token = first text row, TXT_TOKEN_MODE 'cls')
+  long long txt_bstride;
+  const float* text_mask;  // [B, T] (only for TXT_TOKEN_MODE 'mean')
+  int txt_mean, T;
+  int Nz, Nx, D, B;
+  const long long* flag;
+  float logit_scale_exp;
+  float* out;              // [B, n_layers, Nx]; this launch writes slice `layer_slot`
+  int n_layers, layer_slot;
+};
+
+__global__ void __launch_bounds__(256) backbone_logits_kernel(const BackboneLogitParams p) {
+  extern __shared__ float s_tok[];  // [2][D] : vis token, txt token of this batch element
+  const int b = blockIdx.y;
+  const float* vis = p.img + static_cast<long long>(b) * p.img_bstride;
+  const float* txt = p.txt + static_cast<long long>(b) * p.txt_bstride;
+  for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+    s_tok[i] = vis[i];
+    float tv;
+    if (p.txt_mean) {
+      float num = 0.f, den = 0.f;
+      for (int j = 0; j < p.T; ++j) {
+        const float m = p.text_mask[b * p.T + j];
+        num += txt[static_cast<long long>(j) * p.D + i] * m;
+        den += m;
+      }
+      tv = num / den;
+    } else {
+      tv = txt[i];
+    }
+    s_tok[p.D + i] = tv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= p.Nx) return;
+  const float* x = vis + static_cast<long long>(1 + p.Nz + t) * p.D;
+  float xx = 0.f, dv = 0.f, dt = 0.f, nv = 0.f, nt = 0.f;
+  for (int i = lane * 4; i < p.D; i += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    const float4 a = *reinterpret_cast<const float4*>(s_tok + i);
+    const float4 c = *reinterpret_cast<const float4*>(s_tok + p.D + i);
+    xx += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+    dv += xv.x * a.x + xv.y * a.y + xv.z * a.z + xv.w * a.w;
+    dt += xv.x * c.x + xv.y * c.y + xv.z * c.z + xv.w * c.w;
+    nv += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    nt += c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+  }
+  xx = warp_sum(xx); dv = warp_sum(dv); dt = warp_sum(dt); nv = warp_sum(nv); nt = warp_sum(nt);
+  if (lane == 0) {
+    const float inv_x = 1.0f / fmaxf(sqrtf(xx), 1e-12f);
+    const float lv = p.logit_scale_exp * dv * inv_x / fmaxf(sqrtf(nv), 1e-12f);
+    const float lt = p.logit_scale_exp * dt * inv_x / fmaxf(sqrtf(nt), 1e-12f);
+    const long long f = p.flag[b];
+    const float l = (f == 0) ? lv : (f == 1 ? lt : (lv + lt) * 0.5f);
+    p.out[(static_cast<long long>(b) * p.n_layers + p.layer_slot) * p.Nx + t] = l;
+  }
+}
+
+}  // namespace uvlt

@@ -1,0 +1,59 @@
+// Host-side helpers shared by the op-level entry points and the engine: error plumbing, TMA descriptor encoding,
+// kernel launch wrappers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "attention.cuh"
+#include "gemm.cuh"
+
+namespace uvlt {
+
+// thread-local last error text for the C ABI (uvlt_last_error)
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define UVLT_CUDA_OK(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::uvlt::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));                \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+// 3-D tiled bf16 tensor map with 128-byte swizzle.  dims/strides innermost first; box = {64, box_rows, 1}.
+// Returns 0 on success.
+int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_rows);
+
+struct GemmLaunch {
+  CUtensorMap tma_a, tma_w;
+  GemmShape shape;
+  GemmEpilogue ep;
+  int bn;      // 32 / 64 / 128
+  int groups;  // grid.z
+};
+
+// Builds the tensor maps for A [groups][M,K] and W [groups][N,K] (both bf16, K contiguous).
+int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstride, const void* W, long long w_ld,
+                 long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep);
+int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
+int pick_bn(int M, int N, int groups);
+
+struct AttnLaunch {
+  CUtensorMap tma_qkv, tma_vt;
+  AttnParams p;
+  int B;
+  bool v_kmajor;
+};
+int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
+                 int n_pad);
+int attn_launch(const AttnLaunch& a, cudaStream_t stream);
+
+int init_kernel_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation; idempotent
+
+}  // namespace uvlt

@@ -1,0 +1,119 @@
+// Operator-level C-ABI entry points (declared in include/uvlt.h).  They exist so that every kernel of the hot path
+// can be parity-tested in isolation against the oracle through the same boundary the engine uses.
+#include "../../include/uvlt.h"
+#include "host_utils.h"
+#include "rowwise.cuh"
+#include "head.cuh"
+
+using namespace uvlt;
+
+extern "C" {
+
+const char* uvlt_last_error(void) { return get_error(); }
+
+int uvlt_abi_version(void) { return UVLT_ABI_VERSION; }
+
+int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* resid, void* out, int M, int N, int K,
+                 int act, int out_f32, int bn, void* stream) {
+  if (init_kernel_attributes()) return 1;
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.resid = resid;
+  ep.resid_ld = N;
+  ep.act = act;
+  ep.out = out;
+  ep.out_f32 = out_f32;
+  ep.out_ld = N;
+  GemmLaunch g;
+  if (gemm_prepare(&g, A, K, 0, W, K, 0, M, N, K, 1, bn, ep)) return 1;
+  return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,
+                         int act, long long out_ld, long long out_gstride, int bn, void* stream) {
+  if (init_kernel_attributes()) return 1;
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.bias_gstride = N;
+  ep.act = act;
+  ep.out = out;
+  ep.out_f32 = 0;
+  ep.out_ld = out_ld;
+  ep.out_gstride = out_gstride;
+  GemmLaunch g;
+  if (gemm_prepare(&g, A, K, static_cast<long long>(M) * K, W, K, static_cast<long long>(N) * K, M, N, K, groups, bn,
+                   ep))
+    return 1;
+  return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+
+int uvlt_op_attention(const void* qkv, const float* key_bias, void* out, int B, int n, int H, const void* v_t,
+                      int n_pad, void* stream) {
+  if (init_kernel_attributes()) return 1;
+  AttnLaunch a;
+  if (attn_prepare(&a, qkv, B, n, H, key_bias, out, v_t, n_pad)) return 1;
+  return attn_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+int uvlt_op_layernorm(const float* src0, int rows0, const float* src1, int rows1, const float* add0,
+                      const float* add1, int split, float* dst_f32, int dst_mode, void* dst_bf16, const float* gamma,
+                      const float* beta, float eps, int B, int D, void* stream) {
+  LnParams p{};
+  p.src0 = src0; p.src1 = src1; p.rows0 = rows0; p.rows1 = rows1;
+  p.add0 = add0; p.add1 = add1; p.split = split;
+  p.dst_f32 = dst_f32; p.dst_mode = dst_mode;
+  p.dst_bf16 = reinterpret_cast<__nv_bfloat16*>(dst_bf16);
+  p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.total_rows = B * (rows0 + rows1);
+  const int blocks = (p.total_rows + 7) / 8;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (D == 768) layernorm_kernel<6><<<blocks, 256, 0, s>>>(p);
+  else if (D == 1024) layernorm_kernel<8><<<blocks, 256, 0, s>>>(p);
+  else { set_error("layernorm: D must be 768 or 1024"); return 1; }
+  UVLT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int uvlt_op_patch_im2col(const float* tmpl, const float* srch, int B, int Hz, int Hx, void* out, const float* cls,
+                         float* x_stream, int D, void* stream) {
+  PatchParams p{tmpl, srch, B, Hz, Hx, reinterpret_cast<__nv_bfloat16*>(out), cls, x_stream, D};
+  const int Np = (Hz / 16) * (Hz / 16) + (Hx / 16) * (Hx / 16);
+  const long long warps = 3LL * B * Np + B;
+  patch_im2col_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVLT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int uvlt_op_im2col3x3(const void* src, int src_f32, long long src_bstride, long long src_row_off, long long src_ld,
+                      int G, int C, int S, int B, void* dst, void* stream) {
+  Im2col3Params p{src, src_f32, src_bstride, src_row_off, src_ld, G, C, S, B, reinterpret_cast<__nv_bfloat16*>(dst)};
+  const long long warps = 9LL * G * B * S * S;
+  im2col3x3_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVLT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int uvlt_op_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0,
+                       const float* gamma, const float* beta, float* dst_f32, void* dst_bf16, int B, int T, int D,
+                       int vocab, void* stream) {
+  BertEmbedParams p{ids, word, pos, type0, gamma, beta, dst_f32, reinterpret_cast<__nv_bfloat16*>(dst_bf16), T, B * T,
+                    vocab};
+  const int blocks = (B * T + 7) / 8;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (D == 768) bert_embed_kernel<6><<<blocks, 256, 0, s>>>(p);
+  else if (D == 1024) bert_embed_kernel<8><<<blocks, 256, 0, s>>>(p);
+  else { set_error("bert_embed: D must be 768 or 1024"); return 1; }
+  UVLT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int uvlt_op_build_bias(const long long* flag, const float* text_mask, int B, int Nz, int Nx, int T, float* bias_vis,
+                       float* bias_joint, float* bias_bert, void* stream) {
+  BiasParams p{flag, text_mask, B, Nz, Nx, T, bias_vis, bias_joint, bias_bert};
+  const int total = B * (1 + Nz + Nx + T);
+  build_bias_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  UVLT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
