@@ -201,9 +201,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         tmem_wait_ld();
+        const int lim = kv_valid - c * 32;  // columns >= lim were never written by the MMA (stale TMEM)
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          m_blk = fmaxf(m_blk, fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]));
+        for (int i = 0; i < 32; ++i) {
+          const float x = fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]);
+          m_blk = fmaxf(m_blk, i < lim ? x : -INFINITY);
+        }
       }
       const float m_new = fmaxf(m_run, m_blk);          // finite: every block has >= 1 real, unmasked-or-finite key
       const float alpha = exp2f(m_run - m_new);          // 0 on the first block (m_run = -inf)
@@ -217,10 +220,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         tmem_wait_ld();
         uint32_t pk[16];
+        const int lim = kv_valid - c * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]) - m_new);
-          const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, bj[c * 32 + i + 1]) - m_new);
+          float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]) - m_new);
+          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, bj[c * 32 + i + 1]) - m_new);
+          p0 = i < lim ? p0 : 0.0f;       // stale TMEM columns past the last real key must not reach P
+          p1 = i + 1 < lim ? p1 : 0.0f;
           l_blk += p0 + p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
