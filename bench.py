@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the UVLTrack per-frame hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py                                   # N=1: UVLTrack-B 256x256 template / 256x256 search, BBOX mode,
+                                                      #      batch 1, synthetic 500-frame sequence (BASELINE configs[1])
+    python bench.py --batch 32 --mode NLBBOX          # configs[2]
+    torchrun ... bench.py --gpus 8 ...                # one process per GPU, sequences sharded, one all-gather at the end
+    python bench.py --impl reference                  # the CPU arm: numpy port of the reference forward (oracle/)
+
+A "step" is one tracker frame for every sequence of the per-GPU batch.  One JSON line is printed by rank 0:
+  value     frames/s (all GPUs) of forward_test + window merge/argmax with inputs resident in HBM (CUDA events)
+  e2e       frames/s through the reference-facing call surface Tracker.track(): host crop (OpenCV), H2D of the uint8
+            crops from pinned memory, the engine, D2H of the [B,6] result rows, host box bookkeeping, prompt updates
+  roofline  the GEMM kernel (dominant: ~75% of the step) timed live on this step's shapes vs the bf16 tensor peak;
+            roofline_attention is the same for the fused attention kernel
+  cpu_baseline  the numpy oracle of the same frame on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASELINE_FPS_3090 = 60.0  # profile_model.py, UVLTrack-B z128/x256, RTX 3090 (README.md:130-131)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="base", choices=["base", "large"])
+    ap.add_argument("--template-size", type=int, default=256)
+    ap.add_argument("--search-size", type=int, default=256)
+    ap.add_argument("--mode", default="BBOX", choices=["BBOX", "NLBBOX"])
+    ap.add_argument("--batch", type=int, default=1, help="sequences per GPU")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="frames of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    """Measured roofline denominators (driver-written MEASURED_PEAKS.json), else the recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def workload_name(a):
+    return (f"UVLTrack-{'B' if a.arch == 'base' else 'L'} baseline_{a.arch} template {a.template_size}^2 / search "
+            f"{a.search_size}^2 / 40-token text, {a.mode} mode, batch={a.batch} per GPU, synthetic {a.steps}-frame sequence")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def gemm_flops_per_frame(d, skip_text):
+    """Executed GEMM FLOPs (2*MACs) of one sequence-frame: patch embed + transformer linears + head conv GEMMs."""
+    D, Hd, Nv, N, T, F0, L = d.embed_dim, d.mlp_hidden, d.n_visual, d.n_tokens, d.text_len, d.fusion_start, d.depth
+    per_tok = 2 * (D * 3 * D + D * D + 2 * D * Hd)
+    fl = (d.nz + d.nx) * 2 * 768 * D
+    if skip_text:
+        fl += L * Nv * per_tok
+    else:
+        fl += F0 * (Nv + T) * per_tok + (L - F0) * N * per_tok
+    C, SS = d.head_channels, d.nx
+    fl += 2 * SS * 9 * (D * 4 * C + 4 * (C * C // 2 + (C // 2) * (C // 4) + (C // 4) * (C // 8)))
+    return fl
+
+
+def attn_flops_per_frame(d, skip_text):
+    Nv, N, T, F0, L, D = d.n_visual, d.n_tokens, d.text_len, d.fusion_start, d.depth, d.embed_dim
+    if skip_text:
+        return L * 4 * Nv * Nv * D
+    return F0 * (4 * Nv * Nv * D + 4 * T * T * D) + (L - F0) * 4 * N * N * D
+
+
+def kernel_rooflines(dims, B, skip_text, pk):
+    """Times the two tensor-core kernels on this step's shapes: each distinct (M,N,K) GEMM of a layer and the
+    attention launch, replayed from a CUDA graph (device-bound timing, CUDA events on the launching stream)."""
+    import torch
+
+    from uvltrack_b200 import _cabi
+
+    lib = _cabi.load()
+    D, Hd, H = dims.embed_dim, dims.mlp_hidden, dims.num_heads
+    n = dims.n_visual if skip_text else dims.n_tokens
+    M = B * n
+    dev = "cuda"
+    a = torch.randn(M, Hd, device=dev).to(torch.bfloat16)
+    w = torch.randn(max(3 * D, Hd), Hd, device=dev).to(torch.bfloat16) * 0.02
+    bias = torch.zeros(Hd, device=dev)
+    out_b = torch.empty(M, Hd, device=dev, dtype=torch.bfloat16)
+    out_f = torch.zeros(M, D, device=dev)
+    qkv = torch.randn(B, n, 3 * D, device=dev).to(torch.bfloat16)
+    att = torch.empty(B, n, D, device=dev, dtype=torch.bfloat16)
+    shapes = [("qkv", 3 * D, D, 0, 0), ("proj", D, D, 0, 1), ("fc1", Hd, D, 1, 0), ("fc2", D, Hd, 0, 1)]
+    reps = 20
+
+    def timed(fn):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(reps):
+                    fn()
+            g.replay()
+            s.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            g.replay()
+            e1.record(s)
+            s.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    g_time, g_flops, per = 0.0, 0.0, {}
+    for name, N_, K_, act, f32 in shapes:
+        def fn(N_=N_, K_=K_, act=act, f32=f32):
+            _cabi.check(lib.uvlt_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out_f.data_ptr() if f32 else None,
+                                         out_f.data_ptr() if f32 else out_b.data_ptr(), M, N_, K_, act, f32, 0,
+                                         _cabi.current_stream()), "uvlt_op_gemm")
+        t = timed(fn)
+        fl = 2.0 * M * N_ * K_
+        per[name] = {"us": round(t * 1e6, 2), "tflops": round(fl / t / 1e12, 1)}
+        g_time += t
+        g_flops += fl
+
+    def afn():
+        _cabi.check(lib.uvlt_op_attention(qkv.data_ptr(), None, att.data_ptr(), B, n, H, None, 0, _cabi.current_stream()),
+                    "uvlt_op_attention")
+    ta = timed(afn)
+    fa = 4.0 * B * H * n * n * 64
+    peak = pk["bf16_tflops"]
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (qkv+proj+fc1+fc2 of one layer, M=%d)" % M,
+            "achieved": round(g_flops / g_time / 1e12, 2), "peak": peak, "unit": "TFLOP/s",
+            "frac": round(g_flops / g_time / 1e12 / peak, 4), "traffic": None, "peak_source": pk["source"] + " (burst)",
+            "per_shape": per, "avg_launch_us": round(g_time / 4 * 1e6, 2)}
+    roof_a = {"bound": "tensor", "kernel": "attention_kernel (B=%d, H=%d, n=%d)" % (B, H, n),
+              "achieved": round(fa / ta / 1e12, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(fa / ta / 1e12 / peak, 4),
+              "traffic": None, "avg_launch_us": round(ta * 1e6, 2)}
+    return roof, roof_a
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_frames_per_second(dims, mode, frames, B=1):
+    """The oracle (numpy fp32 port of the reference forward + tracker merge) on the host cores."""
+    from oracle import uvlt_oracle as O
+    from uvltrack_b200.weights import synthetic_inputs, synthetic_state_dict
+
+    sd = synthetic_state_dict(dims, seed=0)
+    inp = synthetic_inputs(dims, B, mode, seed=0)
+    window = O.hanning_window(dims.feat_size)
+
+    def one():
+        out = O.forward_test(sd, dims, inp["template"], inp["search"], inp["ids"], inp["text_mask"], inp["prompt"],
+                             inp["flag"].reshape(-1), want_logits=True)
+        for b in range(B):
+            O.track_decode(out["cls_score_test"][b], out["cont_score"][b], out["bbox_map"][b], window)
+
+    one()  # warm-up (BLAS thread pool, page faults)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        one()
+    dt = time.perf_counter() - t0
+    return B * frames / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python/PyTorch and cannot
+    travel to the GPU box, so this arm times its numpy port (oracle/uvlt_oracle.py, pinned to the reference by
+    tests/golden) with every host thread numpy's BLAS will use."""
+    from uvltrack_b200.weights import ModelDims
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims = (ModelDims.base if a.arch == "base" else ModelDims.large)(a.template_size, a.search_size)
+    steps = min(a.steps, 40)
+    t_start = time.perf_counter()
+    fps, dt = cpu_frames_per_second(dims, a.mode, steps, a.batch)
+    line = {
+        "impl": "reference", "metric": "tracker FPS (frames/sec)", "value": round(fps, 3), "unit": "frames/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": 1, "ms_per_step": round(dt / steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "steps_requested": a.steps,
+                   "note": "numpy port of the reference forward_test + tracker merge; steps capped at 40 frames"},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{steps} frames of the same workload, forward_test + window merge, numpy fp32 (BLAS threads = all cores)"},
+        "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(time.perf_counter() - t_start, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from tests.util import synthetic_sequence
+    from uvltrack_b200 import NestedTensor, config, dp
+    from uvltrack_b200.tracker import BatchTracker
+    from uvltrack_b200.weights import ModelDims, synthetic_inputs, synthetic_state_dict
+
+    rank, world, local = dp.init_process_group()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    else:
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device; there is no CPU path")
+    pk = peaks()
+    B = a.batch
+    dims = (ModelDims.base if a.arch == "base" else ModelDims.large)(a.template_size, a.search_size)
+    cfg = config.baseline_cfg(a.arch, a.template_size, a.search_size, mode=a.mode)
+    params = config.parameters(cfg)
+    params.state_dict = synthetic_state_dict(dims, seed=0)
+    tracker = BatchTracker(params, batch=B)
+    eng = tracker.engine
+    skip_text = a.mode == "BBOX"
+
+    # ---- synthetic sequences: one per (rank, slot); frames are shared across slots with different start boxes ----
+    n_frames = a.steps + a.warmup + 1
+    seqs = []
+    for b in range(B):
+        frames, gts = synthetic_sequence(n_frames, seed=rank * 1000 + b)
+        seqs.append((frames, gts))
+    infos = []
+    rng = np.random.default_rng(7 + rank)
+    for b in range(B):
+        info = {"init_bbox": seqs[b][1][0]}
+        if a.mode != "BBOX":
+            k = int(rng.integers(3, 16))
+            info["text_ids"] = [101] + rng.integers(1000, 30000, size=k).tolist() + [102]
+        infos.append(info)
+    tracker.initialize([s[0][0] for s in seqs], infos)
+
+    # ================= value: device-resident forward_test + merge ================================================
+    inp = synthetic_inputs(dims, B, "BBOX" if a.mode == "BBOX" else "NLBBOX", seed=rank)
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()  # noqa: E731
+    ring = [T(np.random.default_rng(100 + i).standard_normal((B, 3, dims.search_size, dims.search_size), dtype=np.float32))
+            for i in range(4)]
+    tmpl, prompt, flag = T(inp["template"]), T(inp["prompt"]), T(inp["flag"])
+    text = NestedTensor(T(inp["ids"]), T(inp["text_mask"]))
+    window = tracker.window_dev
+    dec_out = torch.empty(B, 6, device="cuda")
+
+    def dev_step(i):
+        eng.forward_test(tmpl, ring[i % len(ring)], text, prompt, flag, skip_text=skip_text, clone=False)
+        eng.lib.uvlt_track_decode(eng.h, window.data_ptr(), 1, None, None, dec_out.data_ptr(), None)
+
+    for i in range(max(a.warmup, 3)):
+        dev_step(i)
+    launches_per_step = eng.last_launch_count  # decode only (reset per call) -> recount below
+    eng.forward_test(tmpl, ring[0], text, prompt, flag, skip_text=skip_text, clone=False)
+    launches_per_step = eng.last_launch_count + 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        dev_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([dev_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t.item())
+
+    # ================= e2e: Tracker.track() from host frames =======================================================
+    for t_ in range(1, a.warmup + 1):
+        tracker.track([s[0][t_] for s in seqs])
+    traj = np.zeros((B, a.steps, 4), dtype=np.float32)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_launches = 0
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        res = tracker.track([s[0][a.warmup + 1 + i] for s in seqs])
+        e2e_launches += eng.last_launch_count
+        for b in range(B):
+            traj[b, i] = res[b]["target_bbox"]
+    traj_dev = torch.from_numpy(traj).cuda()
+    all_traj = dp.gather_trajectories(traj_dev, n_sequences=B * world)  # the ONE collective of the run
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clk = clocks.stop()
+    assert all_traj.shape[0] == B * world and bool(torch.isfinite(all_traj).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    value = world * B * a.steps / dev_s
+    e2e = world * B * a.steps / e2e_s
+    roof, roof_a = kernel_rooflines(dims, B, skip_text, pk)
+    g_fl, a_fl = gemm_flops_per_frame(dims, skip_text), attn_flops_per_frame(dims, skip_text)
+    line = {
+        "metric": "tracker FPS (frames/sec)", "value": round(value, 2), "unit": "frames/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(dev_s / a.steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": round(value / BASELINE_FPS_3090, 2) if (a.arch == "base" and a.batch == 1) else None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sequences_per_gpu": B, "total_sequences": B * world,
+                   "skip_dead_text_branch": skip_text,
+                   "l2": "not flushed: every step streams the 273 MB bf16 weight set (> 126 MB L2) and rotates 4 input frames",
+                   "vs_baseline_note": "value / 60 FPS = the reference's RTX-3090 profile_model.py figure for UVLTrack-B "
+                                       "(z128/x256, forward_test only); this workload is the heavier 256/256 shape"},
+        "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": B * dims.search_size ** 2 * 3,
+                "d2h_bytes_per_step": B * 24, "ms_per_step": round(e2e_s / a.steps * 1e3, 4),
+                "path": "BatchTracker.track(): OpenCV crop on host -> pinned uint8 -> uvlt_track_frame_host -> [B,6] rows "
+                        "-> host box update; prompt update every 20 frames; final trajectory all-gather included"},
+        "gpu_launches": int(launches_per_step * a.steps + e2e_launches),
+        "launches_per_step": int(launches_per_step),
+        "clocks": clk, "roofline": roof, "roofline_attention": roof_a,
+        "step_model": {"gemm_gflop_per_frame": round(g_fl / 1e9, 2), "attention_gflop_per_frame": round(a_fl / 1e9, 2),
+                       "achieved_tflops_whole_step": round((g_fl + a_fl) * B / (dev_s / a.steps) / 1e12, 2)},
+    }
+    if not a.no_cpu_baseline:
+        frames = a.cpu_frames or (24 if a.arch == "base" else 8)
+        fps, dt = cpu_frames_per_second(dims, a.mode, frames, 1)
+        line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{frames} frames (batch 1) of the same workload in {dt:.1f} s: numpy fp32 port of "
+                                          "forward_test + window merge (oracle/uvlt_oracle.py), BLAS on all host cores"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

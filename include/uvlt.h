@@ -64,17 +64,21 @@ typedef struct uvlt_config {
   int32_t cont_layers[32]; /* cfg.MODEL.BACKBONE.CONT_LOSS_LAYER */
 } uvlt_config;
 
-/* Replaces build_model(cfg) (lib/models/uvltrack/uvltrack.py:47-57): allocates weight + workspace arenas. */
+/* Replaces build_model(cfg) (lib/models/uvltrack/uvltrack.py:47-57): allocates weight + workspace arenas on the
+ * current CUDA device. */
 UVLT_API int uvlt_create(const uvlt_config* cfg, uvlt_handle* out);
 UVLT_API void uvlt_destroy(uvlt_handle h);
 
-/* Replaces nn.Module.load_state_dict (lib/test/tracker/uvltrack.py:24).  `key` is the reference state_dict key
- * (e.g. "backbone.vit.blocks.3.attn.qkv.weight"); `data` is a HOST pointer to contiguous fp32.  Unknown keys are
- * ignored and reported through the return value 2 (strict=False semantics).  */
+/* Replaces nn.Module.load_state_dict(strict=False) (lib/test/tracker/uvltrack.py:24).  `key` is the reference
+ * state_dict key (e.g. "backbone.vit.blocks.3.attn.qkv.weight"); `data` is a HOST pointer to contiguous fp32.
+ * Returns 0 when the key is consumed, 2 when it is not part of the hot path (ignored), 1 on a shape error. */
 UVLT_API int uvlt_set_weight(uvlt_handle h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
 /* Repack: fp32 -> bf16 GEMM operands, fused BERT q/k/v, conv weights to (ky,kx,c) order with BatchNorm folded
  * (lib/models/heads/utils.py:126-130).  Fails if a required tensor was never set.  Synchronises the device. */
 UVLT_API int uvlt_finalize_weights(uvlt_handle h);
+
+/* options: "graph" (1: replay the layer chain as a CUDA graph, default 1), "bn" (force GEMM tile width, 0 = auto) */
+UVLT_API int uvlt_set_option(uvlt_handle h, const char* name, int32_t value);
 
 typedef struct uvlt_outputs {
   /* all device pointers into the engine's arena, valid until the next forward on this handle; fp32 */
@@ -82,41 +86,67 @@ typedef struct uvlt_outputs {
   const float* cls_score;     /* [B, S, S]   'cls_score' == 'cls_score_test' (JOINT_CLS false) */
   const float* bbox_map;      /* [B, S*S, 4] (cx, cy, w, h) relative to the search crop */
   const float* pred_boxes;    /* [B, 4]      bbox_map at argmax(cls * softmax(cont)[..., 0]) */
-  const float* cont_score;    /* [B, S*S, 3] (2 when softmax_one == 0) */
+  const float* cont_score;    /* [B, S*S, cont_cols] */
   const float* cont_prob;     /* [B, S*S]    softmax(cont_score)[..., 0] */
-  const float* logits;        /* [B, num_cont_layers, S, S] backbone contrastive logits (0 when disabled) */
-  int32_t batch, n_tokens, embed_dim, feat_size;
+  const float* logits;        /* [B, num_cont_layers, S, S] backbone contrastive logits (NULL when not requested) */
+  const float* prompts;       /* [B, 3, D] the prompt the head used */
+  int32_t batch, n_tokens, embed_dim, feat_size, cont_cols, reserved;
 } uvlt_outputs;
+
+/* flags for the forward calls */
+#define UVLT_WANT_LOGITS 1 /* also evaluate the per-layer contrastive logits (training-only consumer) */
+#define UVLT_SKIP_TEXT 2   /* every flag in the batch is 0 (BBOX): text keys are masked in every fusion layer
+                              (modality_unified_feature_extractor.py:47), so the BERT branch and the text rows are
+                              not evaluated; `tokens` text rows are then undefined.  Image-side results are identical. */
 
 /* UVLTrack.forward_test (lib/models/uvltrack/uvltrack.py:41-45).
  *   template [B,3,Hz,Hz] fp32, search [B,3,Hx,Hx] fp32, ids int64 [B,T], text_mask fp32 [B,T] (1 = real token),
  *   prompt fp32 [B,3,D], flag int64 [B] (0 BBOX, 1 NL, 2 NL+BBOX) -- all DEVICE pointers. */
 UVLT_API int uvlt_forward_test(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
-                      const float* text_mask, const float* prompt, const int64_t* flag, int32_t batch,
-                      int32_t want_logits, uvlt_outputs* out, void* stream);
+                               const float* text_mask, const float* prompt, const int64_t* flag, int32_t batch,
+                               int32_t flags, uvlt_outputs* out, void* stream);
 
-/* Backbone only + prompter: UVLTrack.forward_prompt_init / forward_prompt
- * (lib/models/uvltrack/uvltrack.py:26-38, lib/models/heads/utils.py:78-99).  Uses the token stream of the LAST
- * forward on this handle when run_backbone == 0 (forward_prompt semantics: out_dict of an earlier forward_test).
- *   template_mask uint8 [B,Nz], context_mask uint8 [B,Nx] (1 = inside the target box), prompt_out fp32 [B,3,D]. */
-UVLT_API int uvlt_forward_prompt(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
-                        const float* text_mask, const int64_t* flag, const uint8_t* template_mask,
-                        const uint8_t* context_mask, int32_t batch, int32_t run_backbone, float* prompt_out,
-                        void* stream);
+/* UVLTrack.forward (lib/models/uvltrack/uvltrack.py:18-24), the entry point Tracker.grounding() uses
+ * (lib/test/tracker/uvltrack.py:45-62): backbone -> prompter on the batch's own features with the context taken
+ * from sequence (b + B/2) % B (modality_adaptive_box_head.py:130-131) -> head with the two-column cont_score.
+ *   template_mask uint8 [B,Nz], context_mask uint8 [B,Nx] (1 = inside the target box). */
+UVLT_API int uvlt_forward_train(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
+                                const float* text_mask, const int64_t* flag, const uint8_t* template_mask,
+                                const uint8_t* context_mask, int32_t batch, int32_t flags, uvlt_outputs* out,
+                                void* stream);
 
-/* Post-processing of Tracker.track (lib/test/tracker/uvltrack.py:116-121): merge = cls * window * softmax(cont)[0]
- * in float64, argmax, gather.  window: device float64 [S*S].  out: device fp32 [B,6] = cx,cy,w,h,score,index. */
-UVLT_API int uvlt_track_decode(uvlt_handle h, const double* window, int32_t has_cont, float* out, void* stream);
+/* Backbone only (first half of forward_prompt_init, lib/models/uvltrack/uvltrack.py:26-27): fills out->tokens. */
+UVLT_API int uvlt_backbone(uvlt_handle h, const float* tmpl, const float* search, const int64_t* ids,
+                           const float* text_mask, const int64_t* flag, int32_t batch, int32_t flags,
+                           uvlt_outputs* out, void* stream);
 
-/* Same path end to end with HOST buffers (pinned recommended): copies the inputs to the device, runs
- * forward_test + track decode, copies [B,6] results back and synchronises the stream.  This is the call the
- * bench's e2e number is measured through. */
-UVLT_API int uvlt_track_frame_host(uvlt_handle h, const float* tmpl_host, const float* search_host, const int64_t* ids_host,
-                          const float* text_mask_host, const float* prompt_host, const int64_t* flag_host,
-                          const double* window_dev, int32_t batch, int32_t update_template, float* out_host,
-                          void* stream);
+/* box_head.forward_prompt (modality_adaptive_box_head.py:96-106, heads/utils.py:78-99) on a token stream
+ * [B, 1+Nz+Nx+T, D] (fp32 device; NULL = the stream of the last forward on this handle).
+ * prompt_out fp32 [B,3,D] device. */
+UVLT_API int uvlt_forward_prompt(uvlt_handle h, const float* tokens, const int64_t* flag, const float* text_mask,
+                                 const uint8_t* template_mask, const uint8_t* context_mask, int32_t batch,
+                                 float* prompt_out, void* stream);
 
-/* number of kernels the last forward launched (for bench.py's gpu_launches) */
+/* Post-processing of Tracker.track (lib/test/tracker/uvltrack.py:116-121,127-130) on the maps of the last forward:
+ * merge = cls * window * softmax(cont)[...,0] in float64, argmax, gather.
+ *   window: device float64 [S*S] (np.outer(np.hanning(S), np.hanning(S)), tracker :64-68)
+ *   out: device fp32 [B,6] = cx, cy, w, h, score (= cls*cont at the argmax), argmax index.
+ *   max_score (device fp32 [B], in/out, may be NULL) and snapshot (device fp32 [B, N, D], may be NULL): when
+ *   has_cont and score > max_score[b] the token stream of sequence b is copied to snapshot[b] and max_score[b] is
+ *   raised -- the `self.out_dict = out_dict` bookkeeping of tracker :127-130 kept on the device. */
+UVLT_API int uvlt_track_decode(uvlt_handle h, const double* window, int32_t has_cont, float* max_score,
+                               float* snapshot, float* out, void* stream);
+
+/* One tracker step end to end from HOST memory (pinned recommended): copies the raw uint8 RGB search crops
+ * [B,Hx,Hx,3] to the device, fuses Preprocessor_wo_mask (tracker_utils.py:25-29) into the patch embedding, runs
+ * forward_test + uvlt_track_decode, copies the [B,6] result rows back to out_host and synchronises the stream.
+ * tmpl (fp32 [B,3,Hz,Hz]), ids, text_mask, prompt, flag, window, max_score, snapshot are DEVICE pointers. */
+UVLT_API int uvlt_track_frame_host(uvlt_handle h, const uint8_t* search_u8_host, const float* tmpl, const int64_t* ids,
+                                   const float* text_mask, const float* prompt, const int64_t* flag,
+                                   const double* window, int32_t batch, int32_t flags, int32_t has_cont,
+                                   float* max_score, float* snapshot, float* out_host, void* stream);
+
+/* number of kernels the last forward/track call launched (for bench.py's gpu_launches) */
 UVLT_API int uvlt_last_launch_count(uvlt_handle h);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -139,14 +169,15 @@ UVLT_API int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bia
 UVLT_API int uvlt_op_attention(const void* qkv, const float* key_bias, void* out, int B, int n, int H, const void* v_t,
                       int n_pad, void* stream);
 
-/* LayerNorm over rows gathered from two fp32 streams (see csrc/rowwise.cuh LnParams). */
-UVLT_API int uvlt_op_layernorm(const float* src0, int rows0, const float* src1, int rows1, const float* add0,
-                      const float* add1, int split, float* dst_f32, int dst_mode, void* dst_bf16, const float* gamma,
+/* LayerNorm over `rows` rows per sequence of an fp32 token stream (see csrc/rowwise.cuh LnParams). */
+UVLT_API int uvlt_op_layernorm(float* x, long long x_bstride, int x_row_off, int rows, const float* add0,
+                      const float* add1, int split, int dst_mode, void* dst_bf16, const float* gamma,
                       const float* beta, float eps, int B, int D, void* stream);
 
 /* mae_vit.py:92,99,203-214: patchify as im2col (bf16 [B*(Nz+Nx), 768]) + cls rows of the token stream. */
-UVLT_API int uvlt_op_patch_im2col(const float* tmpl, const float* srch, int B, int Hz, int Hx, void* out, const float* cls,
-                         float* x_stream, int D, void* stream);
+UVLT_API int uvlt_op_patch_im2col(const float* tmpl, const float* srch, const uint8_t* tmpl_u8, const uint8_t* srch_u8,
+                         int B, int Hz, int Hx, void* out, const float* cls, float* x_stream, long long x_bstride,
+                         int D, void* stream);
 
 /* 3x3/pad-1 im2col on an SxS token grid, G channel groups of C channels -> bf16 [G][B*S*S][9*C] (ky,kx,c). */
 UVLT_API int uvlt_op_im2col3x3(const void* src, int src_f32, long long src_bstride, long long src_row_off, long long src_ld,
@@ -154,8 +185,8 @@ UVLT_API int uvlt_op_im2col3x3(const void* src, int src_f32, long long src_bstri
 
 /* bert_backbone.py:260-274 */
 UVLT_API int uvlt_op_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0,
-                       const float* gamma, const float* beta, float* dst_f32, void* dst_bf16, int B, int T, int D,
-                       int vocab, void* stream);
+                       const float* gamma, const float* beta, float* dst_f32, long long dst_bstride, int dst_row_off,
+                       void* dst_bf16, int B, int T, int D, int vocab, void* stream);
 
 /* modality_unified_feature_extractor.py:43-50 + bert_backbone.py:746-748 as additive key biases. */
 UVLT_API int uvlt_op_build_bias(const long long* flag, const float* text_mask, int B, int Nz, int Nx, int T, float* bias_vis,

@@ -1,0 +1,92 @@
+"""Host-side mirror of the reference interface: registries, config overlay, crops, masks, box mapping, tokenizer."""
+import numpy as np
+import pytest
+
+import uvltrack_b200 as u
+from uvltrack_b200 import config, preprocess as pp
+from uvltrack_b200.tracker import WordPieceTokenizer, extract_token_from_nlp
+from uvltrack_b200.weights import ModelDims, sincos_pos_embed, synthetic_inputs, synthetic_state_dict
+
+from oracle import uvlt_oracle as O
+
+
+def test_registry_names_match_reference():
+    assert "uvltrack" in u.registry.MODELS
+    assert "modality_unified_feature_extractor" in u.registry.BACKBONES
+    assert "modality_adaptive_box_head" in u.registry.HEADS
+    with pytest.raises(AssertionError):
+        u.registry.MODELS.register("uvltrack", object())
+
+
+def test_config_overlay_semantics():
+    cfg = config.baseline_cfg("base")
+    assert cfg.MODEL.BACKBONE.FUSION_LAYER == [6, 7, 8, 9, 10, 11] and cfg.TEST.UPDATE_INTERVAL == 20
+    with pytest.raises(ValueError, match="not exist in config.py"):
+        config.update_config(cfg, {"MODEL": {"HEAD": {"BOGUS": 1}}})
+    config.update_config(cfg, {"TRAIN": {"ANYTHING_TRAINING_ONLY": 3}})  # training sections pass through
+    d = ModelDims.from_cfg(cfg)
+    assert (d.embed_dim, d.depth, d.num_heads, d.fusion_start, d.nz, d.nx, d.n_tokens) == (768, 12, 12, 6, 64, 256, 361)
+    dl = ModelDims.from_cfg(config.baseline_cfg("large"))
+    assert (dl.embed_dim, dl.depth, dl.num_heads, dl.fusion_start, len(dl.cont_loss_layers)) == (1024, 24, 16, 12, 16)
+    cfg.MODEL.HEAD.CLS_TOKENIZE = True
+    with pytest.raises(NotImplementedError):
+        ModelDims.from_cfg(cfg)
+    p = config.parameters(config.baseline_cfg("base"))
+    assert (p.template_size, p.search_size, p.template_factor, p.search_factor) == (128, 256, 2.0, 4.0)
+
+
+def test_sample_target_geometry():
+    rng = np.random.default_rng(0)
+    im = rng.integers(0, 255, (120, 160, 3), dtype=np.uint8)
+    crop, rf, box = pp.sample_target(im, [60, 40, 20, 10], 4.0, 64)
+    assert crop.shape == (64, 64, 3) and crop.dtype == np.uint8
+    side = int(np.ceil(np.sqrt(200) * 4.0))
+    assert rf == 64 / side
+    assert np.allclose(box, [0.5 - 20 / side / 2, 0.5 - 10 / side / 2, 20 / side, 10 / side])
+    # a crop hanging over the image border is zero padded
+    crop2, _, _ = pp.sample_target(im, [-30, -30, 20, 20], 2.0, 32)
+    assert (crop2 == 0).all()
+    with pytest.raises(Exception, match="Too small"):
+        pp.sample_target(im, [10, 10, 0, 0], 4.0, 64)
+    # identity case: crop == resize target -> pixels copied verbatim
+    crop3, rf3, _ = pp.sample_target(im, [50, 30, 16, 16], 4.0, 64)
+    assert rf3 == 1.0 and np.array_equal(crop3, im[6:70, 26:90])
+
+
+def test_anno2mask_and_box_mapping():
+    m = pp.anno2mask(np.array([[0.25, 0.25, 0.5, 0.5]], dtype=np.float32), 8).reshape(8, 8)
+    assert m[2:6, 2:6].all() and m.sum() == 16
+    tiny = pp.anno2mask(np.array([[0.51, 0.51, 0.01, 0.01]], dtype=np.float32), 8).reshape(8, 8)
+    assert tiny.sum() == 1 and tiny[4, 4]  # the centre cell is always set
+    state = [100.0, 50.0, 40.0, 20.0]
+    box = pp.map_box_back(state, [128.0, 128.0, 40.0, 20.0], 1.0, 256)
+    assert box == [100.0, 50.0, 40.0, 20.0]  # a centred prediction keeps the state
+    assert pp.clip_box([-50, -50, 20, 20], 480, 640, margin=10) == [0, 0, 10, 10]
+    assert pp.clip_box([700, 500, 20, 20], 480, 640, margin=10) == [630, 470, 10, 10]
+    assert pp.map_box_back(state, [1, 2, 3, 4], 0.5, 256) == O.map_box_back(state, [1, 2, 3, 4], 0.5, 256)
+    assert np.array_equal(pp.hanning_window(16), O.hanning_window(16))
+
+
+def test_wordpiece_tokenizer(tmp_path):
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "the", "dog", "##s", "run", "##ning", ",", "white"]
+    path = tmp_path / "vocab.txt"
+    path.write_text("\n".join(vocab) + "\n")
+    tok = WordPieceTokenizer(str(path))
+    assert tok.tokenize("The white dogs, running zebra") == ["the", "white", "dog", "##s", ",", "run", "##ning", "[UNK]"]
+    ids, mask = extract_token_from_nlp(tok, "the dog", 8)
+    assert ids == [2, 4, 5, 3, 0, 0, 0, 0] and mask == [1, 1, 1, 1, 0, 0, 0, 0]
+    ids, mask = extract_token_from_nlp(tok, "dog " * 30, 8)
+    assert len(ids) == 8 and ids[0] == 2 and ids[-1] == 3 and sum(mask) == 8
+
+
+def test_synthetic_weights_are_deterministic_and_complete():
+    d = ModelDims.base(64, 128)
+    a = synthetic_state_dict(d, seed=5)
+    b = synthetic_state_dict(d, seed=5)
+    assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    assert a["backbone.vit.pos_embed_z"].shape == (1, 16, 768) and a["backbone.vit.pos_embed_x"].shape == (1, 64, 768)
+    assert not any("encoder.layer.6." in k for k in a)  # BERT layers >= fusion_start are discarded by the reference
+    pe = sincos_pos_embed(768, 4)
+    assert pe.shape == (16, 768) and np.allclose(pe[0, :192], 0) and np.allclose(pe[0, 192:384], 1)  # sin(0), cos(0)
+    inp = synthetic_inputs(d, 3, "MIXED", seed=1)
+    assert inp["flag"].reshape(-1).tolist() == [0, 1, 2] and inp["text_mask"][0].sum() == 0 and inp["ids"][1, 0] == 101

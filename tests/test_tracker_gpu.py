@@ -1,0 +1,143 @@
+"""Tracker call surface (initialize / track) on a synthetic sequence, teacher-forced against the oracle: every frame
+the oracle evaluates the SAME crop, template, text and prompt the CUDA tracker used and must produce the same box
+(+-1 px in the search crop whenever the oracle's own top-1/top-2 margin is outside the bf16 noise)."""
+import numpy as np
+import pytest
+import torch
+
+from util import rel_l2, synthetic_sequence
+
+from oracle import uvlt_oracle as O
+from uvltrack_b200 import config, preprocess as pp
+from uvltrack_b200.tracker import BatchTracker, get_tracker_class
+from uvltrack_b200.weights import ModelDims, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(z, x, mode, sd):
+    cfg = config.baseline_cfg("base", z, x, mode=mode)
+    p = config.parameters(cfg)
+    p.state_dict = sd
+    return p
+
+
+@pytest.mark.parametrize("mode", ["BBOX", "NLBBOX"])
+def test_track_matches_oracle_teacher_forced(mode):
+    z, x, n = 128, 256, 23
+    dims = ModelDims.base(z, x)
+    sd = synthetic_state_dict(dims, seed=0)
+    frames, gts = synthetic_sequence(n + 1, seed=4)
+    params = _params(z, x, mode, sd)
+    params.cfg.TEST.UPDATE_INTERVAL = 10
+    params.cfg.TEST.THRESHOLD = 0.05
+    tracker = get_tracker_class()(params, "synthetic")
+    info = {"init_bbox": gts[0]}
+    if mode == "NLBBOX":
+        info["text_ids"] = [101, 2023, 3899, 2003, 2652, 102]
+    tracker.initialize(frames[0], info)
+    bt = tracker._bt
+    window = pp.hanning_window(dims.feat_size)
+    ids, mask, flag = bt.ids.cpu().numpy(), bt.text_mask.cpu().numpy(), bt.flag.cpu().numpy()
+    template = bt.template.cpu().numpy()
+
+    # prompt of initialize() vs oracle
+    y_patch, _, y_box = pp.sample_target(frames[0], gts[0], params.search_factor, x)
+    cm0 = pp.anno2mask(y_box.reshape(1, 4), x // 16)
+    p_ref = O.forward_prompt_init(sd, dims, template, pp.normalize_image(y_patch), ids, mask,
+                                  bt.template_mask.cpu().numpy().astype(bool), cm0, flag)
+    assert rel_l2(bt.prompt.cpu().numpy(), p_ref) < 1e-2
+
+    checked = 0
+    for t in range(1, n + 1):
+        state_before = list(bt.state[0])
+        prompt_before = bt.prompt.cpu().numpy().copy()
+        out = tracker.track(frames[t])
+        assert set(out) == {"target_bbox"} and len(out["target_bbox"]) == 4
+        crop, rf, _ = pp.sample_target(frames[t], state_before, params.search_factor, x)
+        ref = O.forward_test(sd, dims, template, pp.normalize_image(crop), ids, mask, prompt_before, flag)
+        box, score, j = O.track_decode(ref["cls_score_test"][0], ref["cont_score"][0], ref["bbox_map"][0], window)
+        merged = ref["cls_score_test"][0].reshape(-1).astype(np.float64) * window * \
+            O.softmax(ref["cont_score"][0])[:, 0].astype(np.float64)
+        top2 = np.sort(merged)[-2:]
+        row = bt.out_np[0]
+        if top2[1] - top2[0] > 2e-2:
+            assert int(row[5]) == j, (t, row, j)
+            assert np.abs(row[:4] - box).max() < 1.0 / 256.0
+            ref_state = O.clip_box(O.map_box_back(state_before, (box * np.float32(x) / np.float32(rf)).tolist(), rf, x),
+                                   frames[t].shape[0], frames[t].shape[1], margin=10)
+            assert np.abs(np.array(out["target_bbox"]) - np.array(ref_state)).max() < 1.0 / rf + 1e-3  # +-1 crop px
+            checked += 1
+    assert checked >= n // 3, f"only {checked} frames had a decisive margin"
+    assert bt.frame_id == n
+
+
+def test_prompt_update_uses_best_frame_snapshot():
+    """tracker :127-138: the prompt is rebuilt every UPDATE_INTERVAL frames from the best-scoring frame since the last
+    update; the device keeps that frame's token stream."""
+    z, x = 128, 256
+    dims = ModelDims.base(z, x)
+    sd = synthetic_state_dict(dims, seed=0)
+    frames, gts = synthetic_sequence(8, seed=9)
+    params = _params(z, x, "BBOX", sd)
+    params.cfg.TEST.UPDATE_INTERVAL = 5
+    params.cfg.TEST.THRESHOLD = 0.0
+    bt = BatchTracker(params, batch=1)
+    bt.initialize([frames[0]], [{"init_bbox": gts[0]}])
+    p0 = bt.prompt.clone()
+    best, best_score, best_crop = None, 0.0, None
+    for t in range(1, 6):
+        state_before = list(bt.state[0])
+        res = bt.track([frames[t]])
+        if t < 5:
+            assert torch.equal(bt.prompt, p0)
+        if res[0]["score"] > best_score:
+            best_score, best = res[0]["score"], bt.out_np[0, :4].copy()
+            best_crop, _, _ = pp.sample_target(frames[t], state_before, params.search_factor, x)
+    assert not torch.equal(bt.prompt, p0) and bt.max_score[0] == 0.0 and float(bt.max_score_dev[0]) == 0.0
+    # oracle: backbone of the best frame -> prompter with the mask of that frame's box
+    info = O.backbone(sd, dims, bt.template.cpu().numpy(), pp.normalize_image(best_crop), bt.ids.cpu().numpy(),
+                      bt.text_mask.cpu().numpy(), bt.flag.cpu().numpy(), want_logits=False)
+    cx, cy, w, h = best
+    cm = pp.anno2mask(np.array([[cx - 0.5 * w, cy - 0.5 * h, w, h]], dtype=np.float32), x // 16)
+    p_ref = O.forward_prompt(sd, dims, info, bt.template_mask.cpu().numpy().astype(bool), cm)
+    assert rel_l2(bt.prompt.cpu().numpy(), p_ref) < 1e-2
+
+
+def test_batch_tracker_equals_single_trackers():
+    """B sequences in one engine call == B single-sequence trackers (bit-identical boxes)."""
+    z, x, n, B = 128, 256, 6, 3
+    dims = ModelDims.base(z, x)
+    sd = synthetic_state_dict(dims, seed=0)
+    seqs = [synthetic_sequence(n + 1, seed=20 + b) for b in range(B)]
+    params = _params(z, x, "BBOX", sd)
+    bt = BatchTracker(params, batch=B)
+    bt.initialize([s[0][0] for s in seqs], [{"init_bbox": s[1][0]} for s in seqs])
+    batch_boxes = [[r["target_bbox"] for r in bt.track([s[0][t] for s in seqs])] for t in range(1, n + 1)]
+    single = BatchTracker(params, batch=1, network=None)
+    for b in range(B):
+        single.initialize([seqs[b][0][0]], [{"init_bbox": seqs[b][1][0]}])
+        for t in range(1, n + 1):
+            box = single.track([seqs[b][0][t]])[0]["target_bbox"]
+            assert box == batch_boxes[t - 1][b], (b, t)
+
+
+def test_uint8_fused_preprocess_equals_float_path():
+    """Raw uint8 crops through uvlt_track_frame_host == Preprocessor_wo_mask on the host + forward_test."""
+    from uvltrack_b200 import NestedTensor
+
+    z, x = 128, 256
+    dims = ModelDims.base(z, x)
+    sd = synthetic_state_dict(dims, seed=0)
+    frames, gts = synthetic_sequence(2, seed=2)
+    params = _params(z, x, "BBOX", sd)
+    bt = BatchTracker(params, batch=1)
+    bt.initialize([frames[0]], [{"init_bbox": gts[0]}])
+    state = list(bt.state[0])
+    bt.track([frames[1]])
+    rows_u8 = bt.out_np.copy()
+    crop, _, _ = pp.sample_target(frames[1], state, params.search_factor, x)
+    out = bt.engine.forward_test(bt.template, torch.from_numpy(pp.normalize_image(crop)).cuda(),
+                                 NestedTensor(bt.ids, bt.text_mask), bt.prompt, bt.flag, skip_text=True)
+    rows_f = bt.engine.track_decode(bt.window_dev)[:1].cpu().numpy()
+    assert np.abs(rows_u8 - rows_f).max() < 1e-5

@@ -35,11 +35,16 @@ class UvltOutputs(C.Structure):
 
     _fields_ = [
         ("tokens", c_void_p), ("cls_score", c_void_p), ("bbox_map", c_void_p), ("pred_boxes", c_void_p),
-        ("cont_score", c_void_p), ("cont_prob", c_void_p), ("logits", c_void_p),
+        ("cont_score", c_void_p), ("cont_prob", c_void_p), ("logits", c_void_p), ("prompts", c_void_p),
         ("batch", c_int32), ("n_tokens", c_int32), ("embed_dim", c_int32), ("feat_size", c_int32),
+        ("cont_cols", c_int32), ("reserved", c_int32),
     ]
 
 
+WANT_LOGITS = 1
+SKIP_TEXT = 2
+
+_P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/uvlt.h declares (tests/test_cabi_symbols.py checks)
 SIGNATURES = {
     "uvlt_abi_version": (c_int, []),
@@ -48,29 +53,24 @@ SIGNATURES = {
     "uvlt_destroy": (None, [c_void_p]),
     "uvlt_set_weight": (c_int, [c_void_p, C.c_char_p, c_void_p, C.POINTER(c_int64), c_int32]),
     "uvlt_finalize_weights": (c_int, [c_void_p]),
-    "uvlt_forward_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
-                                  c_int32, C.POINTER(UvltOutputs), c_void_p]),
-    "uvlt_forward_prompt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_int32, c_int32, c_void_p, c_void_p]),
-    "uvlt_track_decode": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
-    "uvlt_track_frame_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_int32, c_int32, c_void_p, c_void_p]),
+    "uvlt_set_option": (c_int, [c_void_p, C.c_char_p, c_int32]),
+    "uvlt_forward_test": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, C.POINTER(UvltOutputs), _P]),
+    "uvlt_forward_train": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, C.POINTER(UvltOutputs), _P]),
+    "uvlt_backbone": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, C.POINTER(UvltOutputs), _P]),
+    "uvlt_forward_prompt": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, _P, _P]),
+    "uvlt_track_decode": (c_int, [_P, _P, c_int32, _P, _P, _P, _P]),
+    "uvlt_track_frame_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
-    "uvlt_op_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                             c_int, c_void_p]),
-    "uvlt_op_gemm_grouped": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                     c_longlong, c_longlong, c_int, c_void_p]),
-    "uvlt_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "uvlt_op_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                  c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
-    "uvlt_op_patch_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                                     c_void_p]),
-    "uvlt_op_im2col3x3": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p]),
-    "uvlt_op_bert_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_int, c_int, c_int, c_int, c_void_p]),
-    "uvlt_op_build_bias": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+    "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,
+                                     c_int, _P]),
+    "uvlt_op_attention": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),
+    "uvlt_op_layernorm": (c_int, [_P, c_longlong, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_float, c_int,
+                                  c_int, _P]),
+    "uvlt_op_patch_im2col": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, c_longlong, c_int, _P]),
+    "uvlt_op_im2col3x3": (c_int, [_P, c_int, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int, _P, _P]),
+    "uvlt_op_bert_embed": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_longlong, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    "uvlt_op_build_bias": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
 }
 
 

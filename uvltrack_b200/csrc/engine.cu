@@ -1,0 +1,977 @@
+// Engine: UVLTrack.forward_test / forward / forward_prompt / Tracker.track post-processing on one B200, as a fixed
+// schedule of the sm_100a kernels in gemm.cuh / attention.cuh / rowwise.cuh / head.cuh.
+//
+// Data layout in HBM (per engine, sized for cfg.max_batch sequences):
+//   x        fp32 [B, N, D]   residual token stream, N = 1 + Nz + Nx + T, row order [cls | template | search | text]
+//                             (mae_vit.py:214, :196).  Image and text rows of one sequence are adjacent so the fusion
+//                             layers (mae_vit.py:193-200) run over the stream in place with no concat / split.
+//   a        bf16 [B*rows, D] LayerNorm output = A operand of the qkv / fc1 GEMMs (compact: only the rows of the layer)
+//   qkv      bf16 [B*rows, 3D]; att bf16 [B*rows, D]; hid bf16 [B*rows, 4D]
+//   t_*      the same four for the BERT branch, which runs concurrently on a second stream in layers < fusion_start
+//   col*/y*  im2col and activations of the four conv towers of the box head (token-major, tower-concatenated channels)
+// Weights: bf16 [out, in] row-major (nn.Linear layout == K-major B operand), fp32 biases / LayerNorm affine.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/uvlt.h"
+#include "head.cuh"
+#include "host_utils.h"
+#include "rowwise.cuh"
+
+using namespace uvlt;
+
+namespace {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { return static_cast<int64_t>(data.size()); }
+};
+
+struct VitLayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
+  __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+struct BertLayerW {
+  float *qkv_b, *ao_b, *ao_g, *ao_beta, *in_b, *out_b, *out_g, *out_beta;
+  __nv_bfloat16 *qkv_w, *ao_w, *in_w, *out_w;
+};
+
+// every GEMM of one forward at a fixed batch size, tensor maps prebuilt
+struct LayerPlan {
+  GemmLaunch qkv, proj, fc1, fc2;
+};
+struct Plan {
+  int B = 0;
+  bool skip_text = false;
+  GemmLaunch patch;
+  std::vector<LayerPlan> vit;   // depth
+  std::vector<LayerPlan> bert;  // fusion_start
+  GemmLaunch head[4];
+  GemmLaunch pr_fc1, pr_fc2;
+  std::vector<AttnLaunch> vit_attn;  // depth
+  AttnLaunch bert_attn;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [want_logits]
+  int graph_kernels[2] = {0, 0};
+};
+
+}  // namespace
+
+struct uvlt_engine {
+  uvlt_config cfg{};
+  int D, H, L, Hd, Hz, Hx, Nz, Nx, Nv, T, N, S, SS, F0, C, Bm;
+  int device = 0;
+  bool finalized = false;
+  bool use_graph = true;
+  int force_bn = 0;
+  int launch_count = 0;
+
+  std::unordered_map<std::string, HostTensor> staged;
+
+  // arenas
+  std::vector<void*> allocs;
+  // weights
+  __nv_bfloat16* patch_w = nullptr;
+  float *patch_b = nullptr, *pos_tab = nullptr, *cls_tok = nullptr, *modal = nullptr;
+  std::vector<VitLayerW> vit;
+  float *word = nullptr, *bpos = nullptr, *btype0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<BertLayerW> bert;
+  __nv_bfloat16* head_w[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* head_b[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *w5 = nullptr, *b5 = nullptr;
+  float bb_scale = 0.f, head_scale = 0.f, pr_scale = 0.f;
+  float* pr_query = nullptr;
+  __nv_bfloat16 *pr_fc1_w = nullptr, *pr_fc2_w = nullptr;
+  float *pr_fc1_b = nullptr, *pr_fc2_b = nullptr;
+
+  // activations
+  float* x = nullptr;
+  __nv_bfloat16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *pcol = nullptr;
+  __nv_bfloat16 *t_a = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_hid = nullptr;
+  float *bias_vis = nullptr, *bias_joint = nullptr, *bias_bert = nullptr;
+  long long* flag_d = nullptr;
+  float *mask_d = nullptr, *prompt_d = nullptr;
+  __nv_bfloat16 *col[4] = {nullptr, nullptr, nullptr, nullptr}, *y[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *cls_map = nullptr, *bbox_map = nullptr, *cont_score = nullptr, *cont_prob = nullptr, *pred_boxes = nullptr,
+        *logits = nullptr;
+  float *pr_src = nullptr, *pr_src0 = nullptr, *pr_out = nullptr;
+  __nv_bfloat16 *pr_src_bf = nullptr, *pr_hid = nullptr;
+  float* track_out = nullptr;
+  int* snap_flag = nullptr;
+  uint8_t* u8_stage = nullptr;
+
+  cudaStream_t side = nullptr;
+  cudaStream_t cap = nullptr;  // graphs are captured here (the caller's stream may be the legacy default stream)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::map<int, std::unique_ptr<Plan>> plans;  // key = B * 2 + skip_text
+  int last_B = 0;
+  int last_cont_cols = 3;
+};
+
+namespace {
+
+#define ENG_CUDA(expr)                                                                \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e));           \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+int dalloc(uvlt_engine* e, T** p, size_t count) {
+  void* q = nullptr;
+  ENG_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  e->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int alloc_activations(uvlt_engine* e) {
+  const size_t B = e->Bm, N = e->N, D = e->D, Hd = e->Hd, T = e->T, SS = e->SS, C = e->C;
+  if (dalloc(e, &e->x, B * N * D)) return 1;
+  ENG_CUDA(cudaMemset(e->x, 0, B * N * D * sizeof(float)));
+  if (dalloc(e, &e->a, B * N * D) || dalloc(e, &e->qkv, B * N * 3 * D) || dalloc(e, &e->att, B * N * D) ||
+      dalloc(e, &e->hid, B * N * Hd) || dalloc(e, &e->pcol, B * (e->Nz + e->Nx) * 768))
+    return 1;
+  if (dalloc(e, &e->t_a, B * T * D) || dalloc(e, &e->t_qkv, B * T * 3 * D) || dalloc(e, &e->t_att, B * T * D) ||
+      dalloc(e, &e->t_hid, B * T * Hd))
+    return 1;
+  if (dalloc(e, &e->bias_vis, B * e->Nv) || dalloc(e, &e->bias_joint, B * N) || dalloc(e, &e->bias_bert, B * T) ||
+      dalloc(e, &e->flag_d, B) || dalloc(e, &e->mask_d, B * T) || dalloc(e, &e->prompt_d, B * 3 * D))
+    return 1;
+  const size_t cin[4] = {D, C, C / 2, C / 4};
+  const size_t cout[4] = {C, C / 2, C / 4, C / 8};
+  for (int l = 0; l < 4; ++l) {
+    if (dalloc(e, &e->col[l], (l == 0 ? 1 : 4) * B * SS * 9 * cin[l])) return 1;
+    if (dalloc(e, &e->y[l], B * SS * 4 * cout[l])) return 1;
+  }
+  if (dalloc(e, &e->cls_map, B * SS) || dalloc(e, &e->bbox_map, B * SS * 4) || dalloc(e, &e->cont_score, B * SS * 3) ||
+      dalloc(e, &e->cont_prob, B * SS) || dalloc(e, &e->pred_boxes, B * 4) ||
+      dalloc(e, &e->logits, B * std::max(1, e->cfg.num_cont_layers) * SS))
+    return 1;
+  if (dalloc(e, &e->pr_src, B * 3 * D) || dalloc(e, &e->pr_src0, B * 3 * D) || dalloc(e, &e->pr_out, B * 3 * D) ||
+      dalloc(e, &e->pr_src_bf, B * 3 * D) || dalloc(e, &e->pr_hid, B * 3 * Hd))
+    return 1;
+  if (dalloc(e, &e->track_out, B * 6) || dalloc(e, &e->snap_flag, B) ||
+      dalloc(e, &e->u8_stage, B * static_cast<size_t>(e->Hx) * e->Hx * 3))
+    return 1;
+  ENG_CUDA(cudaMemset(e->snap_flag, 0, B * sizeof(int)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------------------------
+const HostTensor* find(uvlt_engine* e, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = e->staged.find(key);
+  if (it == e->staged.end()) {
+    set_error("finalize_weights: missing tensor '" + key + "'");
+    return nullptr;
+  }
+  int64_t n = 1;
+  for (int64_t s : shape) n *= s;
+  if (it->second.numel() != n) {
+    set_error("finalize_weights: tensor '" + key + "' has " + std::to_string(it->second.numel()) +
+              " elements, expected " + std::to_string(n));
+    return nullptr;
+  }
+  return &it->second;
+}
+
+int upload_f32(uvlt_engine* e, float** dst, const float* src, size_t n) {
+  if (dalloc(e, dst, n)) return 1;
+  ENG_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+int upload_bf16(uvlt_engine* e, __nv_bfloat16** dst, const float* src, size_t n) {
+  std::vector<__nv_bfloat16> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(src[i]);
+  if (dalloc(e, dst, n)) return 1;
+  ENG_CUDA(cudaMemcpy(*dst, tmp.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return 0;
+}
+int up_f32(uvlt_engine* e, float** dst, const std::string& key, std::initializer_list<int64_t> shape) {
+  const HostTensor* t = find(e, key, shape);
+  if (!t) return 1;
+  return upload_f32(e, dst, t->data.data(), t->data.size());
+}
+int up_bf16(uvlt_engine* e, __nv_bfloat16** dst, const std::string& key, std::initializer_list<int64_t> shape) {
+  const HostTensor* t = find(e, key, shape);
+  if (!t) return 1;
+  return upload_bf16(e, dst, t->data.data(), t->data.size());
+}
+int scalar_exp(uvlt_engine* e, float* dst, const std::string& key) {
+  const HostTensor* t = find(e, key, {1});
+  if (!t) return 1;
+  *dst = expf(t->data[0]);
+  return 0;
+}
+
+int finalize(uvlt_engine* e) {
+  const int64_t D = e->D, Hd = e->Hd, C = e->C;
+  const std::string v = "backbone.vit.";
+  if (up_bf16(e, &e->patch_w, v + "patch_embed.proj.weight", {D, 3, 16, 16})) return 1;
+  if (up_f32(e, &e->patch_b, v + "patch_embed.proj.bias", {D})) return 1;
+  if (up_f32(e, &e->cls_tok, v + "cls_token", {D})) return 1;
+  if (up_f32(e, &e->modal, v + "modal_embed", {2, D})) return 1;
+  {
+    const HostTensor* pz = find(e, v + "pos_embed_z", {e->Nz, D});
+    const HostTensor* px = find(e, v + "pos_embed_x", {e->Nx, D});
+    if (!pz || !px) return 1;
+    std::vector<float> tab(pz->data);
+    tab.insert(tab.end(), px->data.begin(), px->data.end());
+    if (upload_f32(e, &e->pos_tab, tab.data(), tab.size())) return 1;
+  }
+  e->vit.resize(e->L);
+  for (int i = 0; i < e->L; ++i) {
+    const std::string b = v + "blocks." + std::to_string(i) + ".";
+    VitLayerW& w = e->vit[i];
+    if (up_f32(e, &w.ln1_g, b + "norm1.weight", {D}) || up_f32(e, &w.ln1_b, b + "norm1.bias", {D}) ||
+        up_bf16(e, &w.qkv_w, b + "attn.qkv.weight", {3 * D, D}) || up_f32(e, &w.qkv_b, b + "attn.qkv.bias", {3 * D}) ||
+        up_bf16(e, &w.proj_w, b + "attn.proj.weight", {D, D}) || up_f32(e, &w.proj_b, b + "attn.proj.bias", {D}) ||
+        up_f32(e, &w.ln2_g, b + "norm2.weight", {D}) || up_f32(e, &w.ln2_b, b + "norm2.bias", {D}) ||
+        up_bf16(e, &w.fc1_w, b + "mlp.fc1.weight", {Hd, D}) || up_f32(e, &w.fc1_b, b + "mlp.fc1.bias", {Hd}) ||
+        up_bf16(e, &w.fc2_w, b + "mlp.fc2.weight", {D, Hd}) || up_f32(e, &w.fc2_b, b + "mlp.fc2.bias", {D}))
+      return 1;
+  }
+  if (scalar_exp(e, &e->bb_scale, "backbone.logit_scale")) return 1;
+
+  const std::string t = "backbone.bert.";
+  if (up_f32(e, &e->word, t + "embeddings.word_embeddings.weight", {e->cfg.vocab_size, D})) return 1;
+  if (up_f32(e, &e->bpos, t + "embeddings.position_embeddings.weight", {e->cfg.max_position, D})) return 1;
+  {
+    const HostTensor* tt = find(e, t + "embeddings.token_type_embeddings.weight", {2, D});
+    if (!tt) return 1;
+    if (upload_f32(e, &e->btype0, tt->data.data(), D)) return 1;  // token_type_ids are all zero on this path
+  }
+  if (up_f32(e, &e->emb_g, t + "embeddings.LayerNorm.weight", {D}) ||
+      up_f32(e, &e->emb_b, t + "embeddings.LayerNorm.bias", {D}))
+    return 1;
+  e->bert.resize(e->F0);
+  for (int i = 0; i < e->F0; ++i) {
+    const std::string b = t + "encoder.layer." + std::to_string(i) + ".";
+    BertLayerW& w = e->bert[i];
+    const HostTensor* q = find(e, b + "attention.self.query.weight", {D, D});
+    const HostTensor* k = find(e, b + "attention.self.key.weight", {D, D});
+    const HostTensor* vv = find(e, b + "attention.self.value.weight", {D, D});
+    const HostTensor* qb = find(e, b + "attention.self.query.bias", {D});
+    const HostTensor* kb = find(e, b + "attention.self.key.bias", {D});
+    const HostTensor* vb = find(e, b + "attention.self.value.bias", {D});
+    if (!q || !k || !vv || !qb || !kb || !vb) return 1;
+    std::vector<float> fw(q->data);  // fused [3D, D]: same [which][head][64] output order as the ViT qkv Linear
+    fw.insert(fw.end(), k->data.begin(), k->data.end());
+    fw.insert(fw.end(), vv->data.begin(), vv->data.end());
+    std::vector<float> fb(qb->data);
+    fb.insert(fb.end(), kb->data.begin(), kb->data.end());
+    fb.insert(fb.end(), vb->data.begin(), vb->data.end());
+    if (upload_bf16(e, &w.qkv_w, fw.data(), fw.size()) || upload_f32(e, &w.qkv_b, fb.data(), fb.size())) return 1;
+    if (up_bf16(e, &w.ao_w, b + "attention.output.dense.weight", {D, D}) ||
+        up_f32(e, &w.ao_b, b + "attention.output.dense.bias", {D}) ||
+        up_f32(e, &w.ao_g, b + "attention.output.LayerNorm.weight", {D}) ||
+        up_f32(e, &w.ao_beta, b + "attention.output.LayerNorm.bias", {D}) ||
+        up_bf16(e, &w.in_w, b + "intermediate.dense.weight", {Hd, D}) ||
+        up_f32(e, &w.in_b, b + "intermediate.dense.bias", {Hd}) ||
+        up_bf16(e, &w.out_w, b + "output.dense.weight", {D, Hd}) || up_f32(e, &w.out_b, b + "output.dense.bias", {D}) ||
+        up_f32(e, &w.out_g, b + "output.LayerNorm.weight", {D}) || up_f32(e, &w.out_beta, b + "output.LayerNorm.bias", {D}))
+      return 1;
+  }
+
+  // ---- box head: Conv3x3 + BatchNorm(eval) folded, (ky, kx, c) column order, towers concatenated along N ----
+  const char* towers[4] = {"conv_cls", "conv_offset", "conv_bbox", "conv_bbox_grounding"};
+  const int64_t cin[4] = {D, C, C / 2, C / 4};
+  const int64_t cout[4] = {C, C / 2, C / 4, C / 8};
+  for (int l = 0; l < 4; ++l) {
+    const int64_t K = 9 * cin[l];
+    std::vector<float> w(4 * cout[l] * K), bvec(4 * cout[l]);
+    for (int g = 0; g < 4; ++g) {
+      const std::string p = std::string("box_head.") + towers[g] + "." + std::to_string(l) + ".";
+      const HostTensor* cw = find(e, p + "0.weight", {cout[l], cin[l], 3, 3});
+      const HostTensor* cb = find(e, p + "0.bias", {cout[l]});
+      const HostTensor* gam = find(e, p + "1.weight", {cout[l]});
+      const HostTensor* bet = find(e, p + "1.bias", {cout[l]});
+      const HostTensor* mu = find(e, p + "1.running_mean", {cout[l]});
+      const HostTensor* var = find(e, p + "1.running_var", {cout[l]});
+      if (!cw || !cb || !gam || !bet || !mu || !var) return 1;
+      for (int64_t o = 0; o < cout[l]; ++o) {
+        const float sc = gam->data[o] / sqrtf(var->data[o] + 1e-5f);
+        bvec[g * cout[l] + o] = (cb->data[o] - mu->data[o]) * sc + bet->data[o];
+        float* dst = w.data() + (g * cout[l] + o) * K;
+        for (int64_t c = 0; c < cin[l]; ++c)
+          for (int tap = 0; tap < 9; ++tap) dst[tap * cin[l] + c] = cw->data[(o * cin[l] + c) * 9 + tap] * sc;
+      }
+    }
+    if (upload_bf16(e, &e->head_w[l], w.data(), w.size()) || upload_f32(e, &e->head_b[l], bvec.data(), bvec.size()))
+      return 1;
+  }
+  {
+    const int64_t C4 = C / 8;
+    std::vector<float> w5(7 * C4), b5(7);
+    const int nout[4] = {1, 2, 2, 2};
+    int row = 0;
+    for (int g = 0; g < 4; ++g) {
+      const std::string p = std::string("box_head.") + towers[g] + ".4.";
+      const HostTensor* w = find(e, p + "weight", {nout[g], C4, 1, 1});
+      const HostTensor* b = find(e, p + "bias", {nout[g]});
+      if (!w || !b) return 1;
+      for (int o = 0; o < nout[g]; ++o, ++row) {
+        std::memcpy(w5.data() + row * C4, w->data.data() + o * C4, C4 * sizeof(float));
+        b5[row] = b->data[o];
+      }
+    }
+    if (upload_f32(e, &e->w5, w5.data(), w5.size()) || upload_f32(e, &e->b5, b5.data(), b5.size())) return 1;
+  }
+  if (scalar_exp(e, &e->head_scale, "box_head.logit_scale")) return 1;
+  const std::string pr = "box_head.prompter.";
+  if (scalar_exp(e, &e->pr_scale, pr + "logit_scale")) return 1;
+  if (up_f32(e, &e->pr_query, pr + "query_embed.weight", {3, D}) ||
+      up_bf16(e, &e->pr_fc1_w, pr + "mlp.fc1.weight", {Hd, D}) || up_f32(e, &e->pr_fc1_b, pr + "mlp.fc1.bias", {Hd}) ||
+      up_bf16(e, &e->pr_fc2_w, pr + "mlp.fc2.weight", {D, Hd}) || up_f32(e, &e->pr_fc2_b, pr + "mlp.fc2.bias", {D}))
+    return 1;
+  ENG_CUDA(cudaDeviceSynchronize());
+  e->staged.clear();
+  e->finalized = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------------------------
+int prep(uvlt_engine* e, GemmLaunch* g, const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep,
+         int groups = 1, long long a_gstride = 0, long long w_gstride = 0) {
+  return gemm_prepare(g, A, K, a_gstride, W, K, w_gstride, M, N, K, groups, e->force_bn, ep);
+}
+
+GemmEpilogue ep_bf16(const float* bias, void* out, long long ld, int act) {
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.act = act;
+  ep.out = out;
+  ep.out_f32 = 0;
+  ep.out_ld = ld;
+  return ep;
+}
+// fp32 in-place residual update of `rows` rows per sequence starting at row_off of the [B, N, D] stream
+GemmEpilogue ep_stream(uvlt_engine* e, const float* bias, int rows, int row_off) {
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.resid = e->x;
+  ep.resid_ld = e->D;
+  ep.out = e->x;
+  ep.out_f32 = 1;
+  ep.out_ld = e->D;
+  ep.in_rows_per_b = rows;
+  ep.out_rows_per_b = e->N;
+  ep.out_row_off = row_off;
+  return ep;
+}
+
+Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
+  const int key = B * 2 + (skip_text ? 1 : 0);
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) return it->second.get();
+  auto plan = std::make_unique<Plan>();
+  Plan* p = plan.get();
+  p->B = B;
+  p->skip_text = skip_text;
+  const int D = e->D, Hd = e->Hd, Nv = e->Nv, N = e->N, T = e->T;
+  {
+    GemmEpilogue ep{};
+    ep.bias = e->patch_b;
+    ep.resid = e->pos_tab;
+    ep.resid_ld = D;
+    ep.resid_period = e->Nz + e->Nx;
+    ep.out = e->x;
+    ep.out_f32 = 1;
+    ep.out_ld = D;
+    ep.in_rows_per_b = e->Nz + e->Nx;
+    ep.out_rows_per_b = N;
+    ep.out_row_off = 1;
+    if (prep(e, &p->patch, e->pcol, e->patch_w, B * (e->Nz + e->Nx), D, 768, ep)) return nullptr;
+  }
+  p->vit.resize(e->L);
+  p->vit_attn.resize(e->L);
+  for (int i = 0; i < e->L; ++i) {
+    const bool joint = (i >= e->F0) && !skip_text;
+    const int rows = joint ? N : Nv;
+    const int M = B * rows;
+    const VitLayerW& w = e->vit[i];
+    LayerPlan& lp = p->vit[i];
+    if (prep(e, &lp.qkv, e->a, w.qkv_w, M, 3 * D, D, ep_bf16(w.qkv_b, e->qkv, 3 * D, ACT_NONE))) return nullptr;
+    if (prep(e, &lp.proj, e->att, w.proj_w, M, D, D, ep_stream(e, w.proj_b, rows, 0))) return nullptr;
+    if (prep(e, &lp.fc1, e->a, w.fc1_w, M, Hd, D, ep_bf16(w.fc1_b, e->hid, Hd, ACT_GELU))) return nullptr;
+    if (prep(e, &lp.fc2, e->hid, w.fc2_w, M, D, Hd, ep_stream(e, w.fc2_b, rows, 0))) return nullptr;
+    if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0))
+      return nullptr;
+  }
+  if (!skip_text) {
+    p->bert.resize(e->F0);
+    const int M = B * T;
+    for (int i = 0; i < e->F0; ++i) {
+      const BertLayerW& w = e->bert[i];
+      LayerPlan& lp = p->bert[i];
+      if (prep(e, &lp.qkv, e->t_a, w.qkv_w, M, 3 * D, D, ep_bf16(w.qkv_b, e->t_qkv, 3 * D, ACT_NONE))) return nullptr;
+      if (prep(e, &lp.proj, e->t_att, w.ao_w, M, D, D, ep_stream(e, w.ao_b, T, Nv))) return nullptr;
+      if (prep(e, &lp.fc1, e->t_a, w.in_w, M, Hd, D, ep_bf16(w.in_b, e->t_hid, Hd, ACT_GELU))) return nullptr;
+      if (prep(e, &lp.fc2, e->t_hid, w.out_w, M, D, Hd, ep_stream(e, w.out_b, T, Nv))) return nullptr;
+    }
+    if (attn_prepare(&p->bert_attn, e->t_qkv, B, T, e->H, e->bias_bert, e->t_att, nullptr, 0)) return nullptr;
+  }
+  {
+    const int C = e->C, M = B * e->SS;
+    const int cin[4] = {D, C, C / 2, C / 4};
+    const int cout[4] = {C, C / 2, C / 4, C / 8};
+    // layer 0: one GEMM, the four towers concatenated along N
+    if (prep(e, &p->head[0], e->col[0], e->head_w[0], M, 4 * C, 9 * D, ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU)))
+      return nullptr;
+    for (int l = 1; l < 4; ++l) {
+      GemmEpilogue ep = ep_bf16(e->head_b[l], e->y[l], 4 * cout[l], ACT_RELU);
+      ep.bias_gstride = cout[l];
+      ep.out_gstride = cout[l];
+      const int K = 9 * cin[l];
+      if (prep(e, &p->head[l], e->col[l], e->head_w[l], M, cout[l], K, ep, 4, static_cast<long long>(M) * K,
+               static_cast<long long>(cout[l]) * K))
+        return nullptr;
+    }
+  }
+  {
+    const int M = 3 * B;
+    if (prep(e, &p->pr_fc1, e->pr_src_bf, e->pr_fc1_w, M, Hd, D, ep_bf16(e->pr_fc1_b, e->pr_hid, Hd, ACT_GELU)))
+      return nullptr;
+    GemmEpilogue ep{};
+    ep.bias = e->pr_fc2_b;
+    ep.resid = e->pr_src;
+    ep.resid_ld = D;
+    ep.out = e->pr_out;
+    ep.out_f32 = 1;
+    ep.out_ld = D;
+    if (prep(e, &p->pr_fc2, e->pr_hid, e->pr_fc2_w, M, D, Hd, ep)) return nullptr;
+  }
+  e->plans[key] = std::move(plan);
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// schedule
+// ---------------------------------------------------------------------------------------------------------------
+#define RUN(expr)                       \
+  do {                                  \
+    if (expr) return 1;                 \
+    ++e->launch_count;                  \
+  } while (0)
+
+int ln(uvlt_engine* e, cudaStream_t s, int B, int row_off, int rows, const float* g, const float* b, float eps,
+       int mode, __nv_bfloat16* dst, const float* add0, const float* add1, int split) {
+  LnParams p{};
+  p.x = e->x;
+  p.x_bstride = static_cast<long long>(e->N) * e->D;
+  p.x_row_off = row_off;
+  p.rows = rows;
+  p.add0 = add0;
+  p.add1 = add1;
+  p.split = split;
+  p.dst_mode = mode;
+  p.dst_bf16 = dst;
+  p.gamma = g;
+  p.beta = b;
+  p.eps = eps;
+  p.total_rows = B * rows;
+  if (launch_layernorm(p, e->D, s)) {
+    set_error("layernorm launch failed");
+    return 1;
+  }
+  return 0;
+}
+
+int backbone_logits(uvlt_engine* e, cudaStream_t s, int B, int slot) {
+  BackboneLogitParams p{};
+  p.img = e->x;
+  p.img_bstride = static_cast<long long>(e->N) * e->D;
+  p.txt = e->x + static_cast<long long>(e->Nv) * e->D;
+  p.txt_bstride = p.img_bstride;
+  p.text_mask = e->mask_d;
+  p.txt_mean = e->cfg.txt_token_mean;
+  p.T = e->T;
+  p.Nz = e->Nz; p.Nx = e->Nx; p.D = e->D; p.B = B;
+  p.flag = e->flag_d;
+  p.logit_scale_exp = e->bb_scale;
+  p.out = e->logits;
+  p.n_layers = e->cfg.num_cont_layers;
+  p.layer_slot = slot;
+  dim3 grid((e->Nx + 7) / 8, B);
+  backbone_logits_kernel<<<grid, 256, 2 * e->D * sizeof(float), s>>>(p);
+  if (cudaGetLastError() != cudaSuccess) { set_error("backbone_logits launch failed"); return 1; }
+  return 0;
+}
+
+int bert_layer(uvlt_engine* e, Plan* p, cudaStream_t t, int i) {
+  const int B = p->B, Nv = e->Nv, T = e->T;
+  const BertLayerW& w = e->bert[i];
+  const LayerPlan& lp = p->bert[i];
+  RUN(gemm_launch(lp.qkv, t));
+  RUN(attn_launch(p->bert_attn, t));
+  RUN(gemm_launch(lp.proj, t));  // dense + bias + residual, in place on the text rows
+  RUN(ln(e, t, B, Nv, T, w.ao_g, w.ao_beta, 1e-12f, 2, e->t_a, nullptr, nullptr, 0));
+  RUN(gemm_launch(lp.fc1, t));
+  RUN(gemm_launch(lp.fc2, t));
+  RUN(ln(e, t, B, Nv, T, w.out_g, w.out_beta, 1e-12f, 2, e->t_a, nullptr, nullptr, 0));
+  return 0;
+}
+
+int vit_layer(uvlt_engine* e, Plan* p, cudaStream_t s, int i) {
+  const int B = p->B, Nv = e->Nv, N = e->N;
+  const VitLayerW& w = e->vit[i];
+  const LayerPlan& lp = p->vit[i];
+  const bool fusion = i >= e->F0;
+  const int rows = (fusion && !p->skip_text) ? N : Nv;
+  // fusion layers add the modality embeddings to the stream first and keep them (mae_vit.py:196)
+  RUN(ln(e, s, B, 0, rows, w.ln1_g, w.ln1_b, 1e-6f, fusion ? 1 : 0, e->a, fusion ? e->modal : nullptr,
+         fusion ? e->modal + e->D : nullptr, Nv));
+  RUN(gemm_launch(lp.qkv, s));
+  RUN(attn_launch(p->vit_attn[i], s));
+  RUN(gemm_launch(lp.proj, s));
+  RUN(ln(e, s, B, 0, rows, w.ln2_g, w.ln2_b, 1e-6f, 0, e->a, nullptr, nullptr, 0));
+  RUN(gemm_launch(lp.fc1, s));
+  RUN(gemm_launch(lp.fc2, s));
+  return 0;
+}
+
+// Everything between the input-staging kernels and the head.  Runs on `s`; the BERT branch (bert_backbone.py:383-394)
+// is independent of the ViT branch before the first fusion layer and is forked onto e->side, unless the per-layer
+// contrastive logits are wanted (they read both branches after every layer, so the two then run in lock step).
+int run_layers(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits) {
+  RUN(gemm_launch(p->patch, s));
+  const bool text = !p->skip_text;
+  const bool fork = text && e->F0 > 0 && !want_logits;
+  if (want_logits && !text) {
+    set_error("UVLT_WANT_LOGITS cannot be combined with UVLT_SKIP_TEXT");
+    return 1;
+  }
+  if (fork) {
+    ENG_CUDA(cudaEventRecord(e->ev_fork, s));
+    ENG_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+    for (int i = 0; i < e->F0; ++i)
+      if (bert_layer(e, p, e->side, i)) return 1;
+    ENG_CUDA(cudaEventRecord(e->ev_join, e->side));
+  }
+  int slot = 0;
+  bool joined = !fork;
+  for (int i = 0; i < e->L; ++i) {
+    if (i >= e->F0 && !joined) {
+      ENG_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
+      joined = true;
+    }
+    if (vit_layer(e, p, s, i)) return 1;
+    if (text && !fork && i < e->F0 && bert_layer(e, p, s, i)) return 1;
+    if (want_logits) {
+      bool is_cont = false;
+      for (int k = 0; k < e->cfg.num_cont_layers; ++k) is_cont |= (e->cfg.cont_layers[k] == i);
+      if (is_cont) {
+        RUN(backbone_logits(e, s, p->B, slot));
+        ++slot;
+      }
+    }
+  }
+  if (!joined) ENG_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
+  return 0;
+}
+
+int run_head(uvlt_engine* e, Plan* p, cudaStream_t s, bool train_branch) {
+  const int B = p->B, D = e->D, C = e->C, S = e->S;
+  const int cin[4] = {D, C, C / 2, C / 4};
+  const int cout[4] = {C, C / 2, C / 4, C / 8};
+  for (int l = 0; l < 4; ++l) {
+    Im2col3Params ip{};
+    if (l == 0) {
+      ip.src = e->x; ip.src_f32 = 1;
+      ip.src_bstride = static_cast<long long>(e->N) * D;
+      ip.src_row_off = 1 + e->Nz;
+      ip.src_ld = D;
+      ip.G = 1; ip.C = D;
+    } else {
+      ip.src = e->y[l - 1]; ip.src_f32 = 0;
+      ip.src_bstride = static_cast<long long>(e->SS) * 4 * cout[l - 1];
+      ip.src_row_off = 0;
+      ip.src_ld = 4 * cout[l - 1];
+      ip.G = 4; ip.C = cin[l];
+    }
+    ip.S = S; ip.B = B; ip.dst = e->col[l];
+    if (launch_im2col3x3(ip, s)) { set_error("im2col3x3 launch failed"); return 1; }
+    ++e->launch_count;
+    RUN(gemm_launch(p->head[l], s));
+  }
+  HeadFinalParams hp{};
+  hp.y4 = e->y[3]; hp.C4 = C / 8; hp.w5 = e->w5; hp.b5 = e->b5;
+  hp.x_stream = e->x; hp.x_bstride = static_cast<long long>(e->N) * D; hp.x_row_off = 1 + e->Nz; hp.D = D;
+  hp.prompt = e->prompt_d; hp.flag = e->flag_d; hp.logit_scale_exp = e->head_scale;
+  hp.softmax_one = e->cfg.softmax_one; hp.train_branch = train_branch ? 1 : 0;
+  hp.offset_sigmoid = e->cfg.offset_sigmoid; hp.S = S; hp.B = B;
+  hp.cls_map = e->cls_map; hp.bbox_map = e->bbox_map; hp.cont_score = e->cont_score; hp.cont_prob = e->cont_prob;
+  head_final_kernel<<<(B * e->SS + 7) / 8, 256, 0, s>>>(hp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("head_final launch failed"); return 1; }
+  ++e->launch_count;
+  DecodeParams dp{};
+  dp.cls_map = e->cls_map; dp.cont_prob = e->cont_prob; dp.bbox_map = e->bbox_map; dp.window = nullptr;
+  dp.SS = e->SS; dp.mode = 0; dp.out = e->pred_boxes;
+  decode_kernel<<<B, 256, 0, s>>>(dp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("decode launch failed"); return 1; }
+  ++e->launch_count;
+  e->last_cont_cols = (e->cfg.softmax_one && !train_branch) ? 3 : 2;
+  return 0;
+}
+
+int run_prompter(uvlt_engine* e, Plan* p, cudaStream_t s, const float* tokens, const long long* flag,
+                 const float* text_mask, const uint8_t* tmask, const uint8_t* cmask, int ctx_rot, float* out) {
+  const int B = p->B;
+  PrompterParams pp{};
+  pp.tokens = tokens; pp.bstride = static_cast<long long>(e->N) * e->D;
+  pp.Nz = e->Nz; pp.Nx = e->Nx; pp.Nv = e->Nv; pp.T = e->T; pp.D = e->D; pp.B = B;
+  pp.ctx_rot = ctx_rot; pp.template_mask = tmask; pp.context_mask = cmask; pp.flag = flag;
+  pp.txt_mean = e->cfg.txt_token_mean; pp.text_mask = text_mask; pp.logit_scale_exp = e->pr_scale;
+  pp.query_embed = e->pr_query; pp.src = e->pr_src; pp.src0 = e->pr_src0; pp.src_bf16 = e->pr_src_bf;
+  if (e->Nz + e->Nx > PROMPTER_MAX_N) { set_error("prompter: too many target rows"); return 1; }
+  prompter_pool_kernel<<<B, 256, prompter_smem_bytes(e->D, e->Nz + e->Nx), s>>>(pp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("prompter_pool launch failed"); return 1; }
+  ++e->launch_count;
+  RUN(gemm_launch(p->pr_fc1, s));
+  RUN(gemm_launch(p->pr_fc2, s));
+  const int per_seq = 3 * e->D;
+  prompt_select_kernel<<<(per_seq * B + 255) / 256, 256, 0, s>>>(e->pr_out, e->pr_src0, flag, out, per_seq, B);
+  if (cudaGetLastError() != cudaSuccess) { set_error("prompt_select launch failed"); return 1; }
+  ++e->launch_count;
+  return 0;
+}
+
+int stage_inputs(uvlt_engine* e, cudaStream_t s, int B, const float* tmpl, const float* search, const uint8_t* search_u8,
+                 const long long* ids, const float* text_mask, const float* prompt, const long long* flag,
+                 bool skip_text) {
+  PatchParams pp{tmpl, nullptr, search, search_u8, B, e->Hz, e->Hx, e->pcol, e->cls_tok, e->x,
+                 static_cast<long long>(e->N) * e->D, e->D};
+  if (launch_patch_im2col(pp, s)) { set_error("patch_im2col launch failed"); return 1; }
+  ++e->launch_count;
+  BiasParams bp{flag, text_mask, B, e->Nz, e->Nx, e->T, e->bias_vis, e->bias_joint, e->bias_bert,
+                e->flag_d, e->mask_d, prompt, e->prompt_d, B * 3 * e->D};
+  if (launch_build_bias(bp, s)) { set_error("build_bias launch failed"); return 1; }
+  ++e->launch_count;
+  if (!skip_text) {
+    BertEmbedParams ep{ids, e->word, e->bpos, e->btype0, e->emb_g, e->emb_b, e->x,
+                       static_cast<long long>(e->N) * e->D, e->Nv, e->t_a, e->T, B * e->T, e->cfg.vocab_size};
+    if (launch_bert_embed(ep, e->D, s)) { set_error("bert_embed launch failed"); return 1; }
+    ++e->launch_count;
+  }
+  return 0;
+}
+
+// layers (+ head) either replayed from a CUDA graph or launched directly
+int run_core(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits, bool with_head) {
+  if (!e->use_graph || !with_head) {
+    if (run_layers(e, p, s, want_logits)) return 1;
+    if (with_head && run_head(e, p, s, false)) return 1;
+    return 0;
+  }
+  const int gi = want_logits ? 1 : 0;
+  if (!p->graph[gi]) {
+    const int before = e->launch_count;
+    cudaGraph_t g = nullptr;
+    ENG_CUDA(cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
+    int rc = run_layers(e, p, e->cap, want_logits);
+    if (!rc) rc = run_head(e, p, e->cap, false);
+    const cudaError_t ce = cudaStreamEndCapture(e->cap, &g);
+    if (rc || ce != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (!rc) set_error(std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
+      return 1;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&p->graph[gi], g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) {
+      p->graph[gi] = nullptr;
+      set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie));
+      return 1;
+    }
+    p->graph_kernels[gi] = e->launch_count - before;  // kernels recorded into the graph
+    e->launch_count = before;
+  }
+  ENG_CUDA(cudaGraphLaunch(p->graph[gi], s));
+  e->launch_count += p->graph_kernels[gi];
+  return 0;
+}
+
+int check_batch(uvlt_engine* e, int B) {
+  if (!e->finalized) { set_error("weights not finalized: call uvlt_finalize_weights first"); return 1; }
+  if (B < 1 || B > e->Bm) { set_error("batch out of range (max_batch = " + std::to_string(e->Bm) + ")"); return 1; }
+  return 0;
+}
+
+void fill_outputs(uvlt_engine* e, int B, uvlt_outputs* out, bool logits) {
+  if (!out) return;
+  out->tokens = e->x;
+  out->cls_score = e->cls_map;
+  out->bbox_map = e->bbox_map;
+  out->pred_boxes = e->pred_boxes;
+  out->cont_score = e->cont_score;
+  out->cont_prob = e->cont_prob;
+  out->logits = logits ? e->logits : nullptr;
+  out->prompts = e->prompt_d;
+  out->batch = B;
+  out->n_tokens = e->N;
+  out->embed_dim = e->D;
+  out->feat_size = e->S;
+  out->cont_cols = e->last_cont_cols;
+  out->reserved = 0;
+}
+
+int track_decode(uvlt_engine* e, cudaStream_t s, int B, const double* window, int has_cont, float* max_score,
+                 float* snapshot, float* out) {
+  DecodeParams dp{};
+  dp.cls_map = e->cls_map;
+  dp.cont_prob = has_cont ? e->cont_prob : nullptr;
+  dp.bbox_map = e->bbox_map;
+  dp.window = window;
+  dp.SS = e->SS;
+  dp.mode = 1;
+  dp.out = out;
+  const bool snap = has_cont && max_score && snapshot;
+  dp.max_score = snap ? max_score : nullptr;
+  dp.snap_flag = snap ? e->snap_flag : nullptr;
+  decode_kernel<<<B, 256, 0, s>>>(dp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("track decode launch failed"); return 1; }
+  ++e->launch_count;
+  if (snap) {
+    const long long per_seq4 = static_cast<long long>(e->N) * e->D / 4;
+    dim3 grid(32, B);
+    snapshot_kernel<<<grid, 256, 0, s>>>(e->x, snapshot, e->snap_flag, per_seq4);
+    if (cudaGetLastError() != cudaSuccess) { set_error("snapshot launch failed"); return 1; }
+    ++e->launch_count;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvlt_create(const uvlt_config* cfg, uvlt_handle* out) {
+  if (!cfg || !out) { set_error("uvlt_create: null argument"); return 1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("uvlt_create: no CUDA device (this library has no CPU path)");
+    return 1;
+  }
+  if (cfg->embed_dim != 768 && cfg->embed_dim != 1024) { set_error("embed_dim must be 768 or 1024"); return 1; }
+  if (cfg->embed_dim != cfg->num_heads * 64) { set_error("head dim must be 64"); return 1; }
+  if (cfg->template_size % 16 || cfg->search_size % 16 || cfg->template_size <= 0 || cfg->search_size <= 0) {
+    set_error("template/search size must be positive multiples of 16");
+    return 1;
+  }
+  if (cfg->head_channels % 256 || cfg->mlp_hidden % 128 || cfg->fusion_start < 0 || cfg->fusion_start > cfg->depth ||
+      cfg->max_batch < 1 || cfg->text_len < 1 || cfg->num_cont_layers < 0 || cfg->num_cont_layers > 32) {
+    set_error("uvlt_create: unsupported configuration");
+    return 1;
+  }
+  auto* e = new uvlt_engine();
+  e->cfg = *cfg;
+  e->D = cfg->embed_dim; e->H = cfg->num_heads; e->L = cfg->depth; e->Hd = cfg->mlp_hidden;
+  e->Hz = cfg->template_size; e->Hx = cfg->search_size;
+  e->Nz = (e->Hz / 16) * (e->Hz / 16); e->Nx = (e->Hx / 16) * (e->Hx / 16);
+  e->Nv = 1 + e->Nz + e->Nx; e->T = cfg->text_len; e->N = e->Nv + e->T;
+  e->S = e->Hx / 16; e->SS = e->S * e->S; e->F0 = cfg->fusion_start; e->C = cfg->head_channels; e->Bm = cfg->max_batch;
+  if (e->N > ATT_MAX_KV) { set_error("sequence too long for the attention kernel"); delete e; return 1; }
+  cudaGetDevice(&e->device);
+  if (init_kernel_attributes() || alloc_activations(e) ||
+      cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    if (!*get_error()) set_error("uvlt_create: CUDA resource creation failed");
+    uvlt_destroy(e);
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+void uvlt_destroy(uvlt_handle e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : e->plans)
+    for (auto& g : kv.second->graph)
+      if (g) cudaGraphExecDestroy(g);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->cap) cudaStreamDestroy(e->cap);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  delete e;
+}
+
+int uvlt_set_weight(uvlt_handle e, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+  if (!e || !key || !data) { set_error("uvlt_set_weight: null argument"); return 1; }
+  const std::string k(key);
+  // parameters the per-frame path never touches: final ViT norm, BERT pooler, prompter q/kv/proj/norm,
+  // BERT layers >= fusion_start, BatchNorm counters, the coordinate buffer (regenerated in-kernel)
+  auto has = [&](const char* s) { return k.find(s) != std::string::npos; };
+  if (has("backbone.vit.norm.") || has("bert.pooler.") || has("prompter.q.") || has("prompter.kv.") ||
+      has("prompter.proj.") || has("prompter.norm.") || has("num_batches_tracked") || has("coodinate"))
+    return 2;
+  if (has("bert.encoder.layer.")) {
+    const int li = atoi(k.c_str() + k.find("layer.") + 6);
+    if (li >= e->F0) return 2;
+  }
+  if (!(has("backbone.") || has("box_head."))) return 2;
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.assign(data, data + n);
+  e->staged[k] = std::move(t);
+  e->finalized = false;
+  return 0;
+}
+
+int uvlt_finalize_weights(uvlt_handle e) {
+  if (!e) { set_error("null handle"); return 1; }
+  return finalize(e);
+}
+
+int uvlt_set_option(uvlt_handle e, const char* name, int32_t value) {
+  if (!e || !name) { set_error("uvlt_set_option: null argument"); return 1; }
+  const std::string n(name);
+  if (n == "graph") e->use_graph = value != 0;
+  else if (n == "bn") {
+    if (value != 0 && value != 32 && value != 64 && value != 128) { set_error("bn must be 0/32/64/128"); return 1; }
+    e->force_bn = value;
+    cudaDeviceSynchronize();
+    for (auto& kv : e->plans)
+      for (auto& g : kv.second->graph)
+        if (g) cudaGraphExecDestroy(g);
+    e->plans.clear();
+  } else { set_error("unknown option '" + n + "'"); return 1; }
+  return 0;
+}
+
+int uvlt_forward_test(uvlt_handle e, const float* tmpl, const float* search, const int64_t* ids, const float* text_mask,
+                      const float* prompt, const int64_t* flag, int32_t B, int32_t flags, uvlt_outputs* out,
+                      void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!tmpl || !search || !ids || !text_mask || !prompt || !flag) { set_error("uvlt_forward_test: null input"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool skip_text = flags & UVLT_SKIP_TEXT, logits = flags & UVLT_WANT_LOGITS;
+  Plan* p = get_plan(e, B, skip_text);
+  if (!p) return 1;
+  e->launch_count = 0;
+  if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, prompt,
+                   reinterpret_cast<const long long*>(flag), skip_text))
+    return 1;
+  if (run_core(e, p, s, logits, true)) return 1;
+  e->last_B = B;
+  fill_outputs(e, B, out, logits);
+  return 0;
+}
+
+int uvlt_backbone(uvlt_handle e, const float* tmpl, const float* search, const int64_t* ids, const float* text_mask,
+                  const int64_t* flag, int32_t B, int32_t flags, uvlt_outputs* out, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!tmpl || !search || !ids || !text_mask || !flag) { set_error("uvlt_backbone: null input"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool skip_text = flags & UVLT_SKIP_TEXT, logits = flags & UVLT_WANT_LOGITS;
+  Plan* p = get_plan(e, B, skip_text);
+  if (!p) return 1;
+  e->launch_count = 0;
+  if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, nullptr,
+                   reinterpret_cast<const long long*>(flag), skip_text))
+    return 1;
+  if (run_core(e, p, s, logits, false)) return 1;
+  e->last_B = B;
+  fill_outputs(e, B, out, logits);
+  return 0;
+}
+
+int uvlt_forward_train(uvlt_handle e, const float* tmpl, const float* search, const int64_t* ids,
+                       const float* text_mask, const int64_t* flag, const uint8_t* template_mask,
+                       const uint8_t* context_mask, int32_t B, int32_t flags, uvlt_outputs* out, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!tmpl || !search || !ids || !text_mask || !flag || !template_mask || !context_mask) {
+    set_error("uvlt_forward_train: null input");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool logits = flags & UVLT_WANT_LOGITS;
+  Plan* p = get_plan(e, B, false);
+  if (!p) return 1;
+  e->launch_count = 0;
+  if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, nullptr,
+                   reinterpret_cast<const long long*>(flag), false))
+    return 1;
+  if (run_layers(e, p, s, logits)) return 1;
+  if (run_prompter(e, p, s, e->x, e->flag_d, e->mask_d, template_mask, context_mask, B / 2, e->prompt_d)) return 1;
+  if (run_head(e, p, s, true)) return 1;
+  e->last_B = B;
+  fill_outputs(e, B, out, logits);
+  return 0;
+}
+
+int uvlt_forward_prompt(uvlt_handle e, const float* tokens, const int64_t* flag, const float* text_mask,
+                        const uint8_t* template_mask, const uint8_t* context_mask, int32_t B, float* prompt_out,
+                        void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!flag || !template_mask || !context_mask || !prompt_out) { set_error("uvlt_forward_prompt: null input"); return 1; }
+  if (e->cfg.txt_token_mean && !text_mask) { set_error("uvlt_forward_prompt: text_mask required in 'mean' mode"); return 1; }
+  Plan* p = get_plan(e, B, false);
+  if (!p) return 1;
+  e->launch_count = 0;
+  return run_prompter(e, p, static_cast<cudaStream_t>(stream), tokens ? tokens : e->x,
+                      reinterpret_cast<const long long*>(flag), text_mask, template_mask, context_mask, 0, prompt_out);
+}
+
+int uvlt_track_decode(uvlt_handle e, const double* window, int32_t has_cont, float* max_score, float* snapshot,
+                      float* out, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (e->last_B < 1) { set_error("uvlt_track_decode: no forward has run on this handle"); return 1; }
+  if (!window || !out) { set_error("uvlt_track_decode: null argument"); return 1; }
+  e->launch_count = 0;
+  return track_decode(e, static_cast<cudaStream_t>(stream), e->last_B, window, has_cont, max_score, snapshot, out);
+}
+
+int uvlt_track_frame_host(uvlt_handle e, const uint8_t* search_u8_host, const float* tmpl, const int64_t* ids,
+                          const float* text_mask, const float* prompt, const int64_t* flag, const double* window,
+                          int32_t B, int32_t flags, int32_t has_cont, float* max_score, float* snapshot,
+                          float* out_host, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!search_u8_host || !tmpl || !ids || !text_mask || !prompt || !flag || !window || !out_host) {
+    set_error("uvlt_track_frame_host: null argument");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool skip_text = flags & UVLT_SKIP_TEXT;
+  Plan* p = get_plan(e, B, skip_text);
+  if (!p) return 1;
+  e->launch_count = 0;
+  const size_t bytes = static_cast<size_t>(B) * e->Hx * e->Hx * 3;
+  ENG_CUDA(cudaMemcpyAsync(e->u8_stage, search_u8_host, bytes, cudaMemcpyHostToDevice, s));
+  if (stage_inputs(e, s, B, tmpl, nullptr, e->u8_stage, reinterpret_cast<const long long*>(ids), text_mask, prompt,
+                   reinterpret_cast<const long long*>(flag), skip_text))
+    return 1;
+  if (run_core(e, p, s, false, true)) return 1;
+  e->last_B = B;
+  if (track_decode(e, s, B, window, has_cont, max_score, snapshot, e->track_out)) return 1;
+  ENG_CUDA(cudaMemcpyAsync(out_host, e->track_out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ENG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int uvlt_last_launch_count(uvlt_handle e) { return e ? e->launch_count : 0; }
+
+}  // extern "C"

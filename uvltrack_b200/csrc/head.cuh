@@ -25,6 +25,7 @@ struct HeadFinalParams {
   const long long* flag;    // [B]
   float logit_scale_exp;
   int softmax_one;
+  int train_branch;         // 1: two-column cont_score of the training branch (modality_adaptive_box_head.py:132-137)
   int offset_sigmoid;
   int S, B;
   float* cls_map;           // [B, SS]
@@ -33,7 +34,7 @@ struct HeadFinalParams {
   float* cont_prob;         // [B, SS]  softmax(cont_score)[..., 0]
 };
 
-__global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p) {
+static __global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SS = p.S * p.S;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -90,13 +91,14 @@ __global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p
   const float c1 = p.logit_scale_exp * d1 * inv_x / fmaxf(sqrtf(n1), 1e-12f);
   const float c2 = p.logit_scale_exp * d2 * inv_x / fmaxf(sqrtf(n2), 1e-12f);
   float s1, prob0;
-  if (p.softmax_one) {
+  const bool three = p.softmax_one && !p.train_branch;
+  if (three) {
     s1 = fmaxf(fmaxf(c1, c2), 0.0f);
     const float m = fmaxf(fmaxf(c0, s1), 0.0f);
     const float e0 = expf(c0 - m), e1 = expf(s1 - m), e2 = expf(0.0f - m);
     prob0 = e0 / (e0 + e1 + e2);
   } else {
-    s1 = fmaxf(c1, c2);
+    s1 = p.softmax_one ? fmaxf(fmaxf(c1, c2), 0.0f) : fmaxf(c1, c2);
     const float m = fmaxf(c0, s1);
     const float e0 = expf(c0 - m), e1 = expf(s1 - m);
     prob0 = e0 / (e0 + e1);
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p
     bb.z = bw;
     bb.w = bh;
     *reinterpret_cast<float4*>(p.bbox_map + static_cast<long long>(r) * 4) = bb;
-    if (p.softmax_one) {
+    if (three) {
       float* cs = p.cont_score + static_cast<long long>(r) * 3;
       cs[0] = c0; cs[1] = s1; cs[2] = 0.0f;
     } else {
@@ -136,9 +138,11 @@ struct DecodeParams {
   const double* window;    // [SS] (mode 1)
   int SS, mode;
   float* out;              // mode 0: [B, 4]; mode 1: [B, 6]
+  float* max_score;        // mode 1, optional [B]: raised when the new score beats it (tracker :127-130)
+  int* snap_flag;          // mode 1, optional [B]: 1 when the token stream of this sequence must be snapshotted
 };
 
-__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
+static __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
   __shared__ double s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x;
@@ -172,8 +176,14 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
       float* o = p.out + b * 6;
       o[0] = bb.x; o[1] = bb.y; o[2] = bb.z; o[3] = bb.w;
       const float q = p.cont_prob ? p.cont_prob[b * p.SS + best_i] : 1.0f;
-      o[4] = p.cls_map[b * p.SS + best_i] * q;
+      const float score = p.cls_map[b * p.SS + best_i] * q;
+      o[4] = score;
       o[5] = static_cast<float>(best_i);
+      if (p.snap_flag) {
+        const bool better = p.max_score && score > p.max_score[b];
+        p.snap_flag[b] = better ? 1 : 0;
+        if (better) p.max_score[b] = score;
+      }
     }
   }
 }
@@ -196,7 +206,7 @@ struct BackboneLogitParams {
   int n_layers, layer_slot;
 };
 
-__global__ void __launch_bounds__(256) backbone_logits_kernel(const BackboneLogitParams p) {
+static __global__ void __launch_bounds__(256) backbone_logits_kernel(const BackboneLogitParams p) {
   extern __shared__ float s_tok[];  // [2][D] : vis token, txt token of this batch element
   const int b = blockIdx.y;
   const float* vis = p.img + static_cast<long long>(b) * p.img_bstride;
@@ -242,6 +252,225 @@ __global__ void __launch_bounds__(256) backbone_logits_kernel(const BackboneLogi
     const float l = (f == 0) ? lv : (f == 1 ? lt : (lv + lt) * 0.5f);
     p.out[(static_cast<long long>(b) * p.n_layers + p.layer_slot) * p.Nx + t] = l;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Conditional snapshot of the token stream (the `self.out_dict = out_dict` of lib/test/tracker/uvltrack.py:127-130)
+// ----------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) snapshot_kernel(const float* __restrict__ x, float* __restrict__ snap,
+                                                       const int* __restrict__ snap_flag, long long per_seq4) {
+  const int b = blockIdx.y;
+  if (!snap_flag[b]) return;
+  const float4* src = reinterpret_cast<const float4*>(x) + b * per_seq4;
+  float4* dst = reinterpret_cast<float4*>(snap) + b * per_seq4;
+  for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < per_seq4; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// Prompter, pooling half (heads/utils.py:45-99, DistributionBasedCrossAttention.forward without its MLP):
+// one CTA per sequence.
+//   token     = [vis, txt, (vis+txt)/2][flag]                      (modality_adaptive_box_head.py:97-102)
+//   tgt       = [template rows | context rows]; sim = e^{ls} <token^, tgt^_j>
+//   tgt_score = softmax(sim | tgt_mask), bgd_score = softmax(sim | ~tgt_mask)
+//   threshold = first ascending-sorted bgd_score whose running sum reaches 0.25 (1.0 if none) -> distractor mask
+//   src       = [tgt_token, dis_token, bgd_token] + src_,  src_ = query_embed (+ token on slot 0)
+// ----------------------------------------------------------------------------------------------
+struct PrompterParams {
+  const float* tokens;          // [B, N, D]
+  long long bstride;
+  int Nz, Nx, Nv, T, D, B;
+  int ctx_rot;                  // context rows come from sequence (b + ctx_rot) % B
+  const uint8_t* template_mask; // [B, Nz]
+  const uint8_t* context_mask;  // [B, Nx]
+  const long long* flag;        // [B]
+  int txt_mean;
+  const float* text_mask;       // [B, T] (TXT_TOKEN_MODE 'mean')
+  float logit_scale_exp;
+  const float* query_embed;     // [3, D]
+  float* src;                   // [B, 3, D]
+  float* src0;                  // [B, 3, D]
+  __nv_bfloat16* src_bf16;      // [3B, D]
+};
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// masked softmax over sim[0..n): logits = keep[j] ? sim[j] : -1e20, written to out[0..n)
+__device__ __forceinline__ void masked_softmax(const float* sim, int n, float* out, float* red, int mode,
+                                               const uint8_t* m0, const uint8_t* m1) {
+  // mode 0: keep = m0 (target)         mode 1: keep = !m0 (background)
+  // mode 2: keep = !m0 && !m1 (pure background)    mode 3: keep = !m0-filled logit && m1 ... see below
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float l = sim[j];
+    if (mode == 0) l = m0[j] ? l : -1e20f;
+    else {
+      l = m0[j] ? -1e20f : l;                 // bgd_logit
+      if (mode == 2) l = m1[j] ? -1e20f : l;  // masked_fill(dis_mask)
+      if (mode == 3) l = m1[j] ? l : -1e20f;  // masked_fill(~dis_mask)
+    }
+    out[j] = l;
+    mx = fmaxf(mx, l);
+  }
+  mx = block_reduce(mx, true, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float e = expf(out[j] - mx);
+    out[j] = e;
+    sum += e;
+  }
+  sum = block_reduce(sum, false, red);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = out[j] / sum;
+  __syncthreads();
+}
+
+constexpr int PROMPTER_MAX_N = 2048;  // Nz + Nx <= 2048 (384^2 + 384^2 -> 1152)
+
+static __global__ void __launch_bounds__(256) prompter_pool_kernel(const PrompterParams p) {
+  extern __shared__ float sm[];
+  const int n = p.Nz + p.Nx;
+  float* tok = sm;                       // [D]
+  float* sim = tok + p.D;                // [n]
+  float* w_tgt = sim + n;                // [n]
+  float* w_bgd = w_tgt + n;              // [n]
+  float* w_dis = w_bgd + n;              // [n]
+  float* sorted = w_dis + n;             // [PROMPTER_MAX_N]
+  float* red = sorted + PROMPTER_MAX_N;  // [8]
+  uint8_t* tmask = reinterpret_cast<uint8_t*>(red + 8);  // [n]
+  uint8_t* dmask = tmask + n;                              // [n]
+  __shared__ float s_thr;
+
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const long long f = p.flag[b];
+  const float* xb = p.tokens + static_cast<long long>(b) * p.bstride;
+  const float* xc = p.tokens + static_cast<long long>((b + p.ctx_rot) % p.B) * p.bstride;
+  const float* vis = xb;
+  const float* txt = xb + static_cast<long long>(p.Nv) * p.D;
+
+  // ---- token ----
+  float nrm = 0.f;
+  for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+    float tv;
+    if (p.txt_mean) {
+      float num = 0.f, den = 0.f;
+      for (int j = 0; j < p.T; ++j) {
+        const float m = p.text_mask[b * p.T + j];
+        num += txt[static_cast<long long>(j) * p.D + i] * m;
+        den += m;
+      }
+      tv = num / den;
+    } else {
+      tv = txt[i];
+    }
+    const float v = vis[i];
+    const float t = (f == 0) ? v : (f == 1 ? tv : (v + tv) / 2.0f);
+    tok[i] = t;
+    nrm += t * t;
+  }
+  nrm = block_reduce(nrm, false, red);
+  const float inv_tok = 1.0f / fmaxf(sqrtf(nrm), 1e-12f);
+  for (int j = threadIdx.x; j < n; j += blockDim.x)
+    tmask[j] = (j < p.Nz) ? p.template_mask[b * p.Nz + j] : p.context_mask[b * p.Nx + (j - p.Nz)];
+  __syncthreads();
+
+  // ---- similarity: one warp per target row ----
+  for (int j = warp; j < n; j += nwarp) {
+    const float* row = (j < p.Nz) ? xb + static_cast<long long>(1 + j) * p.D
+                                  : xc + static_cast<long long>(1 + p.Nz + (j - p.Nz)) * p.D;
+    float d = 0.f, rr = 0.f;
+    for (int i = lane * 4; i < p.D; i += 128) {
+      const float4 r4 = *reinterpret_cast<const float4*>(row + i);
+      const float4 t4 = *reinterpret_cast<const float4*>(tok + i);
+      d += r4.x * t4.x + r4.y * t4.y + r4.z * t4.z + r4.w * t4.w;
+      rr += r4.x * r4.x + r4.y * r4.y + r4.z * r4.z + r4.w * r4.w;
+    }
+    d = warp_sum(d); rr = warp_sum(rr);
+    if (lane == 0) sim[j] = d * inv_tok / fmaxf(sqrtf(rr), 1e-12f) * p.logit_scale_exp;
+  }
+  __syncthreads();
+
+  // ---- target / background distributions ----
+  masked_softmax(sim, n, w_tgt, red, 0, tmask, nullptr);
+  masked_softmax(sim, n, w_bgd, red, 1, tmask, nullptr);  // bgd_score (before the split)
+
+  // ---- ascending bitonic sort of bgd_score, sequential running sum, threshold ----
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  for (int j = threadIdx.x; j < npad; j += blockDim.x) sorted[j] = (j < n) ? w_bgd[j] : INFINITY;
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int s = k >> 1; s > 0; s >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int ixj = i ^ s;
+        if (ixj > i) {
+          const float a = sorted[i], c = sorted[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { sorted[i] = c; sorted[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    float cum = 0.f, thr = 1.0f;
+    for (int j = 0; j < n; ++j) {
+      cum += sorted[j];
+      if (!(cum < 0.25f)) { thr = sorted[j]; break; }
+    }
+    s_thr = thr;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) dmask[j] = w_bgd[j] >= thr ? 1 : 0;
+  __syncthreads();
+  masked_softmax(sim, n, w_bgd, red, 2, tmask, dmask);  // pure background
+  masked_softmax(sim, n, w_dis, red, 3, tmask, dmask);  // distractors
+
+  // ---- three weighted sums over the target rows + query embeddings ----
+  for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float* row = (j < p.Nz) ? xb + static_cast<long long>(1 + j) * p.D
+                                    : xc + static_cast<long long>(1 + p.Nz + (j - p.Nz)) * p.D;
+      const float v = row[i];
+      a0 += w_tgt[j] * v;
+      a1 += w_dis[j] * v;
+      a2 += w_bgd[j] * v;
+    }
+    const float q0 = p.query_embed[i] + tok[i];
+    const float q1 = p.query_embed[p.D + i];
+    const float q2 = p.query_embed[2 * p.D + i];
+    const long long o = (static_cast<long long>(b) * 3) * p.D + i;
+    p.src0[o] = q0; p.src0[o + p.D] = q1; p.src0[o + 2 * p.D] = q2;
+    const float s0 = a0 + q0, s1 = a1 + q1, s2 = a2 + q2;
+    p.src[o] = s0; p.src[o + p.D] = s1; p.src[o + 2 * p.D] = s2;
+    p.src_bf16[o] = __float2bfloat16(s0);
+    p.src_bf16[o + p.D] = __float2bfloat16(s1);
+    p.src_bf16[o + 2 * p.D] = __float2bfloat16(s2);
+  }
+}
+
+inline size_t prompter_smem_bytes(int D, int n) {
+  return sizeof(float) * (static_cast<size_t>(D) + 4 * n + PROMPTER_MAX_N + 8) + 2 * static_cast<size_t>(n) + 16;
+}
+
+// switcher of heads/utils.py:93-97: [src, src_, src][flag]
+static __global__ void __launch_bounds__(256) prompt_select_kernel(const float* mlp_out, const float* src0,
+                                                            const long long* flag, float* out, int per_seq, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_seq * B) return;
+  const int b = i / per_seq;
+  out[i] = (flag[b] == 1) ? src0[i] : mlp_out[i];
 }
 
 }  // namespace uvlt

@@ -55,64 +55,45 @@ int uvlt_op_attention(const void* qkv, const float* key_bias, void* out, int B, 
   return attn_launch(a, static_cast<cudaStream_t>(stream));
 }
 
-int uvlt_op_layernorm(const float* src0, int rows0, const float* src1, int rows1, const float* add0,
-                      const float* add1, int split, float* dst_f32, int dst_mode, void* dst_bf16, const float* gamma,
-                      const float* beta, float eps, int B, int D, void* stream) {
+int uvlt_op_layernorm(float* x, long long x_bstride, int x_row_off, int rows, const float* add0, const float* add1,
+                      int split, int dst_mode, void* dst_bf16, const float* gamma, const float* beta, float eps, int B,
+                      int D, void* stream) {
   LnParams p{};
-  p.src0 = src0; p.src1 = src1; p.rows0 = rows0; p.rows1 = rows1;
-  p.add0 = add0; p.add1 = add1; p.split = split;
-  p.dst_f32 = dst_f32; p.dst_mode = dst_mode;
+  p.x = x; p.x_bstride = x_bstride; p.x_row_off = x_row_off; p.rows = rows;
+  p.add0 = add0; p.add1 = add1; p.split = split; p.dst_mode = dst_mode;
   p.dst_bf16 = reinterpret_cast<__nv_bfloat16*>(dst_bf16);
   p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.total_rows = B * (rows0 + rows1);
-  const int blocks = (p.total_rows + 7) / 8;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (D == 768) layernorm_kernel<6><<<blocks, 256, 0, s>>>(p);
-  else if (D == 1024) layernorm_kernel<8><<<blocks, 256, 0, s>>>(p);
-  else { set_error("layernorm: D must be 768 or 1024"); return 1; }
-  UVLT_CUDA_OK(cudaGetLastError());
-  return 0;
+  p.total_rows = B * rows;
+  return launch_layernorm(p, D, static_cast<cudaStream_t>(stream));
 }
 
-int uvlt_op_patch_im2col(const float* tmpl, const float* srch, int B, int Hz, int Hx, void* out, const float* cls,
-                         float* x_stream, int D, void* stream) {
-  PatchParams p{tmpl, srch, B, Hz, Hx, reinterpret_cast<__nv_bfloat16*>(out), cls, x_stream, D};
-  const int Np = (Hz / 16) * (Hz / 16) + (Hx / 16) * (Hx / 16);
-  const long long warps = 3LL * B * Np + B;
-  patch_im2col_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  UVLT_CUDA_OK(cudaGetLastError());
-  return 0;
+int uvlt_op_patch_im2col(const float* tmpl, const float* srch, const uint8_t* tmpl_u8, const uint8_t* srch_u8, int B,
+                         int Hz, int Hx, void* out, const float* cls, float* x_stream, long long x_bstride, int D,
+                         void* stream) {
+  PatchParams p{tmpl, tmpl_u8, srch, srch_u8, B, Hz, Hx, reinterpret_cast<__nv_bfloat16*>(out), cls, x_stream,
+                x_bstride, D};
+  return launch_patch_im2col(p, static_cast<cudaStream_t>(stream));
 }
 
 int uvlt_op_im2col3x3(const void* src, int src_f32, long long src_bstride, long long src_row_off, long long src_ld,
                       int G, int C, int S, int B, void* dst, void* stream) {
   Im2col3Params p{src, src_f32, src_bstride, src_row_off, src_ld, G, C, S, B, reinterpret_cast<__nv_bfloat16*>(dst)};
-  const long long warps = 9LL * G * B * S * S;
-  im2col3x3_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  UVLT_CUDA_OK(cudaGetLastError());
+  if (launch_im2col3x3(p, static_cast<cudaStream_t>(stream))) { set_error("im2col3x3 launch failed"); return 1; }
   return 0;
 }
 
 int uvlt_op_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0,
-                       const float* gamma, const float* beta, float* dst_f32, void* dst_bf16, int B, int T, int D,
-                       int vocab, void* stream) {
-  BertEmbedParams p{ids, word, pos, type0, gamma, beta, dst_f32, reinterpret_cast<__nv_bfloat16*>(dst_bf16), T, B * T,
-                    vocab};
-  const int blocks = (B * T + 7) / 8;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (D == 768) bert_embed_kernel<6><<<blocks, 256, 0, s>>>(p);
-  else if (D == 1024) bert_embed_kernel<8><<<blocks, 256, 0, s>>>(p);
-  else { set_error("bert_embed: D must be 768 or 1024"); return 1; }
-  UVLT_CUDA_OK(cudaGetLastError());
-  return 0;
+                       const float* gamma, const float* beta, float* dst_f32, long long dst_bstride, int dst_row_off,
+                       void* dst_bf16, int B, int T, int D, int vocab, void* stream) {
+  BertEmbedParams p{ids, word, pos, type0, gamma, beta, dst_f32, dst_bstride, dst_row_off,
+                    reinterpret_cast<__nv_bfloat16*>(dst_bf16), T, B * T, vocab};
+  return launch_bert_embed(p, D, static_cast<cudaStream_t>(stream));
 }
 
 int uvlt_op_build_bias(const long long* flag, const float* text_mask, int B, int Nz, int Nx, int T, float* bias_vis,
                        float* bias_joint, float* bias_bert, void* stream) {
-  BiasParams p{flag, text_mask, B, Nz, Nx, T, bias_vis, bias_joint, bias_bert};
-  const int total = B * (1 + Nz + Nx + T);
-  build_bias_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  UVLT_CUDA_OK(cudaGetLastError());
+  BiasParams p{flag, text_mask, B, Nz, Nx, T, bias_vis, bias_joint, bias_bert, nullptr, nullptr, nullptr, nullptr, 0};
+  if (launch_build_bias(p, static_cast<cudaStream_t>(stream))) { set_error("build_bias launch failed"); return 1; }
   return 0;
 }
 

@@ -13,19 +13,19 @@ namespace uvlt {
 //   BERT (bert_backbone.py:240-244, eps 1e-12, post-LN): the normalised value replaces the stream (dst_mode 2).
 // ----------------------------------------------------------------------------------------------
 struct LnParams {
-  const float* src0;   // [B, rows0, D]
-  const float* src1;   // [B, rows1, D] or nullptr
-  int rows0, rows1;    // rows per batch element in src0 / src1 (output has rows0 + rows1 rows per element)
-  const float* add0;   // [D] added to output rows [0, split) of every element, or nullptr
-  const float* add1;   // [D] added to output rows [split, rows0+rows1), or nullptr
+  float* x;            // fp32 token stream; row (b, i) lives at x + b * x_bstride + (x_row_off + i) * D
+  long long x_bstride; // elements between sequences
+  int x_row_off;       // first row of the normalised range inside a sequence
+  int rows;            // rows per sequence
+  const float* add0;   // [D] added to rows [0, split) of every sequence before normalising, or nullptr
+  const float* add1;   // [D] added to rows [split, rows), or nullptr
   int split;
-  float* dst_f32;      // [B, rows0+rows1, D] or nullptr
-  int dst_mode;        // 0 none, 1 write (x + add) [pre-norm], 2 write normalised value [post-LN]
-  __nv_bfloat16* dst_bf16;  // [B*(rows0+rows1), D] or nullptr
+  int dst_mode;        // 0: stream untouched, 1: write (x + add) back [pre-LN fusion layers], 2: write LN(x) back [post-LN]
+  __nv_bfloat16* dst_bf16;  // compact [B*rows, D] GEMM A operand, or nullptr
   const float* gamma;
   const float* beta;
   float eps;
-  int total_rows;      // B * (rows0 + rows1)
+  int total_rows;      // B * rows
 };
 
 template <int NV>  // D = NV * 128  (768 -> 6, 1024 -> 8)
@@ -34,10 +34,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= p.total_rows) return;
-  const int rows = p.rows0 + p.rows1;
-  const int b = r / rows, i = r - b * rows;
-  const float* src = (i < p.rows0) ? p.src0 + (static_cast<long long>(b) * p.rows0 + i) * D
-                                   : p.src1 + (static_cast<long long>(b) * p.rows1 + (i - p.rows0)) * D;
+  const int b = r / p.rows, i = r - b * p.rows;
+  float* src = p.x + static_cast<long long>(b) * p.x_bstride + static_cast<long long>(p.x_row_off + i) * D;
   const float* add = (i < p.split) ? p.add0 : p.add1;
   float4 x[NV];
 #pragma unroll
@@ -49,8 +47,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       x[k].x += a.x; x[k].y += a.y; x[k].z += a.z; x[k].w += a.w;
     }
   }
-  float* dstf = p.dst_f32 ? p.dst_f32 + static_cast<long long>(r) * D : nullptr;
-  if (dstf && p.dst_mode == 1) {
+  float* dstf = src;
+  if (p.dst_mode == 1 && add) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(dstf + k * 128 + lane * 4) = x[k];
   }
@@ -74,7 +72,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     y.y = (x[k].y - mean) * rstd * g.y + be.y;
     y.z = (x[k].z - mean) * rstd * g.z + be.z;
     y.w = (x[k].w - mean) * rstd * g.w + be.w;
-    if (dstf && p.dst_mode == 2) *reinterpret_cast<float4*>(dstf + k * 128 + lane * 4) = y;
+    if (p.dst_mode == 2) *reinterpret_cast<float4*>(dstf + k * 128 + lane * 4) = y;
     if (p.dst_bf16) {
       uint2 u;
       u.x = pack_bf16x2(y.x, y.y);
@@ -94,8 +92,10 @@ struct BertEmbedParams {
   const float* type0;       // [D]   (token_type_ids are all zero on this path)
   const float* gamma;
   const float* beta;
-  float* dst_f32;           // [B*T, D]
-  __nv_bfloat16* dst_bf16;  // [B*T, D]
+  float* dst_f32;           // token stream; row (b, t) at dst_f32 + b * dst_bstride + (dst_row_off + t) * D
+  long long dst_bstride;
+  int dst_row_off;
+  __nv_bfloat16* dst_bf16;  // compact [B*T, D] or nullptr
   int T, total_rows, vocab;
 };
 
@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) bert_embed_kernel(const BertEmbedParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= p.total_rows) return;
-  const int t = r % p.T;
+  const int t = r % p.T, bb = r / p.T;
+  float* dstf = p.dst_f32 + static_cast<long long>(bb) * p.dst_bstride + static_cast<long long>(p.dst_row_off + t) * D;
   long long id = p.ids[r];
   id = id < 0 ? 0 : (id >= p.vocab ? p.vocab - 1 : id);
   const float* w = p.word + id * D;
@@ -139,11 +140,13 @@ __global__ void __launch_bounds__(256) bert_embed_kernel(const BertEmbedParams p
     y.y = (x[k].y - mean) * rstd * g.y + be.y;
     y.z = (x[k].z - mean) * rstd * g.z + be.z;
     y.w = (x[k].w - mean) * rstd * g.w + be.w;
-    *reinterpret_cast<float4*>(p.dst_f32 + static_cast<long long>(r) * D + k * 128 + lane * 4) = y;
-    uint2 u;
-    u.x = pack_bf16x2(y.x, y.y);
-    u.y = pack_bf16x2(y.z, y.w);
-    *reinterpret_cast<uint2*>(p.dst_bf16 + static_cast<long long>(r) * D + k * 128 + lane * 4) = u;
+    *reinterpret_cast<float4*>(dstf + k * 128 + lane * 4) = y;
+    if (p.dst_bf16) {
+      uint2 u;
+      u.x = pack_bf16x2(y.x, y.y);
+      u.y = pack_bf16x2(y.z, y.w);
+      *reinterpret_cast<uint2*>(p.dst_bf16 + static_cast<long long>(r) * D + k * 128 + lane * 4) = u;
+    }
   }
 }
 
@@ -151,54 +154,84 @@ __global__ void __launch_bounds__(256) bert_embed_kernel(const BertEmbedParams p
 // Patch im2col (mae_vit.py:92,99: Conv2d(3, D, 16, stride 16) == GEMM over 3*16*16 = 768 inputs).
 // Output row (b, p) with p in [0, Nz) template patches then [Nz, Nz+Nx) search patches, row-major (h, w);
 // column order c*256 + ky*16 + kx matches weight.view(D, -1).  Also writes the cls rows of the token stream.
-// One warp per (row, channel): 16 rows x 16 px of one patch channel.
+// Each image comes either as fp32 NCHW already normalised (forward_test operator API) or as the tracker's raw
+// uint8 HWC RGB crop, in which case Preprocessor_wo_mask (lib/test/tracker/tracker_utils.py:25-29:
+// ((x / 255) - mean) / std in fp32) is fused here.  One warp per patch.
 // ----------------------------------------------------------------------------------------------
 struct PatchParams {
-  const float* tmpl;   // [B, 3, Hz, Hz]
-  const float* srch;   // [B, 3, Hx, Hx]
-  int B, Hz, Hx;       // image sides (multiples of 16)
-  __nv_bfloat16* out;  // [B*(Nz+Nx), 768]
-  const float* cls;    // [D]
-  float* x_stream;     // [B, 1+Nz+Nx, D] (only row 0 of each element is written here)
+  const float* tmpl;       // [B, 3, Hz, Hz] or nullptr
+  const uint8_t* tmpl_u8;  // [B, Hz, Hz, 3] or nullptr
+  const float* srch;       // [B, 3, Hx, Hx] or nullptr
+  const uint8_t* srch_u8;  // [B, Hx, Hx, 3] or nullptr
+  int B, Hz, Hx;           // image sides (multiples of 16)
+  __nv_bfloat16* out;      // [B*(Nz+Nx), 768]
+  const float* cls;        // [D]
+  float* x_stream;         // token stream; row 0 of each sequence receives the cls token
+  long long x_bstride;
   int D;
 };
 
-__global__ void __launch_bounds__(256) patch_im2col_kernel(const PatchParams p) {
+static __global__ void __launch_bounds__(256) patch_im2col_kernel(const PatchParams p) {
   const int gz = p.Hz >> 4, gx = p.Hx >> 4;
   const int Nz = gz * gz, Nx = gx * gx;
   const int rows = p.B * (Nz + Nx);
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (warp_global < rows * 3) {
-    const int r = warp_global / 3, c = warp_global - r * 3;
+  if (r < rows) {
     const int b = r / (Nz + Nx), pi = r - b * (Nz + Nx);
-    const float* img;
-    int side, py, px;
-    if (pi < Nz) {
-      img = p.tmpl + (static_cast<long long>(b) * 3 + c) * p.Hz * p.Hz;
-      side = p.Hz; py = pi / gz; px = pi - py * gz;
-    } else {
-      const int q = pi - Nz;
-      img = p.srch + (static_cast<long long>(b) * 3 + c) * p.Hx * p.Hx;
-      side = p.Hx; py = q / gx; px = q - py * gx;
-    }
-    __nv_bfloat16* dst = p.out + static_cast<long long>(r) * 768 + c * 256;
-    // 256 px = 64 float4; lane handles float4 index lane and lane+32: ky = idx/4, kx4 = idx%4
+    const bool is_z = pi < Nz;
+    const int side = is_z ? p.Hz : p.Hx;
+    const int g = is_z ? gz : gx;
+    const int q = is_z ? pi : pi - Nz;
+    const int py = q / g, px = q - py * g;
+    const float* f32 = is_z ? p.tmpl : p.srch;
+    const uint8_t* u8 = is_z ? p.tmpl_u8 : p.srch_u8;
+    __nv_bfloat16* dst = p.out + static_cast<long long>(r) * 768;
+    if (f32) {
+      const float* img = f32 + static_cast<long long>(b) * 3 * side * side;
+      // 3 channels x 16 rows x 4 float4 = 192 float4 per patch -> 6 per lane
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int idx = lane + h * 32;
-      const int ky = idx >> 2, kx = (idx & 3) * 4;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(img + static_cast<long long>(py * 16 + ky) * side + px * 16 + kx));
-      uint2 u;
-      u.x = pack_bf16x2(v.x, v.y);
-      u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(dst + ky * 16 + kx) = u;
+      for (int h = 0; h < 6; ++h) {
+        const int idx = lane + h * 32;
+        const int c = idx >> 6, ky = (idx >> 2) & 15, kx = (idx & 3) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            img + (static_cast<long long>(c) * side + py * 16 + ky) * side + px * 16 + kx));
+        uint2 u;
+        u.x = pack_bf16x2(v.x, v.y);
+        u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + c * 256 + ky * 16 + kx) = u;
+      }
+    } else {
+      // HWC bytes: a patch row is 48 contiguous bytes; lane -> (ky = lane / 2, 8 pixels = 24 bytes)
+      const uint8_t* img = u8 + static_cast<long long>(b) * side * side * 3;
+      const int ky = lane >> 1, kx0 = (lane & 1) * 8;
+      const uint8_t* src = img + (static_cast<long long>(py * 16 + ky) * side + px * 16 + kx0) * 3;
+      const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(src));
+      const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(src + 8));
+      const uint2 w2 = __ldg(reinterpret_cast<const uint2*>(src + 16));
+      const uint32_t words[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+      const float mean[3] = {0.485f, 0.456f, 0.406f};
+      const float stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int byte = i * 3 + c;
+          const float raw = static_cast<float>((words[byte >> 2] >> ((byte & 3) * 8)) & 0xffu);
+          v[i] = (raw / 255.0f - mean[c]) / stdv[c];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst + c * 256 + ky * 16 + kx0) = u;
+      }
     }
   } else {
     // trailing warps: cls token rows
-    const int w = warp_global - rows * 3;
+    const int w = r - rows;
     if (w < p.B) {
-      float* dst = p.x_stream + static_cast<long long>(w) * (1 + Nz + Nx) * p.D;
+      float* dst = p.x_stream + static_cast<long long>(w) * p.x_bstride;
       for (int i = lane * 4; i < p.D; i += 128)
         *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(p.cls + i));
     }
@@ -221,7 +254,7 @@ struct Im2col3Params {
   __nv_bfloat16* dst;     // [G][B*S*S][9*C]
 };
 
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const Im2col3Params p) {
+static __global__ void __launch_bounds__(256) im2col3x3_kernel(const Im2col3Params p) {
   const int lane = threadIdx.x & 31;
   const long long wg = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int SS = p.S * p.S;
@@ -268,11 +301,21 @@ struct BiasParams {
   float* bias_vis;    // [B, 1+Nz+Nx]
   float* bias_joint;  // [B, 1+Nz+Nx+T]
   float* bias_bert;   // [B, T]
+  // optional staging of the per-call inputs into engine-owned buffers (so a captured CUDA graph sees fixed addresses)
+  long long* flag_copy;    // [B] or nullptr
+  float* mask_copy;        // [B, T] or nullptr
+  const float* prompt;     // [B, 3, D] or nullptr
+  float* prompt_copy;      // [B, 3, D]
+  int prompt_elems;        // B * 3 * D
 };
 
-__global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams p) {
+static __global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams p) {
   const int Nv = 1 + p.Nz + p.Nx, N = Nv + p.T;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.prompt) {
+    for (int j = i; j < p.prompt_elems; j += gridDim.x * blockDim.x) p.prompt_copy[j] = p.prompt[j];
+  }
+  if (p.flag_copy && i < p.B) p.flag_copy[i] = p.flag[i];
   if (i >= p.B * N) return;
   const int b = i / N, k = i - b * N;
   const long long f = p.flag[b];
@@ -287,7 +330,42 @@ __global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams p) {
     const float keep = m * (f != 0 ? 1.0f : 0.0f);      // reference: text.mask * (flag != 0), then .bool()
     p.bias_joint[i] = (keep != 0.0f) ? 0.0f : NEG;
     p.bias_bert[b * p.T + j] = (1.0f - m) * -10000.0f;
+    if (p.mask_copy) p.mask_copy[b * p.T + j] = m;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launch helpers (return 0 on success; the caller reports cudaGetLastError)
+// ----------------------------------------------------------------------------------------------
+inline int launch_layernorm(const LnParams& p, int D, cudaStream_t s) {
+  const int blocks = (p.total_rows + 7) / 8;
+  if (D == 768) layernorm_kernel<6><<<blocks, 256, 0, s>>>(p);
+  else if (D == 1024) layernorm_kernel<8><<<blocks, 256, 0, s>>>(p);
+  else return 1;
+  return cudaGetLastError() != cudaSuccess;
+}
+inline int launch_bert_embed(const BertEmbedParams& p, int D, cudaStream_t s) {
+  const int blocks = (p.total_rows + 7) / 8;
+  if (D == 768) bert_embed_kernel<6><<<blocks, 256, 0, s>>>(p);
+  else if (D == 1024) bert_embed_kernel<8><<<blocks, 256, 0, s>>>(p);
+  else return 1;
+  return cudaGetLastError() != cudaSuccess;
+}
+inline int launch_patch_im2col(const PatchParams& p, cudaStream_t s) {
+  const int Np = (p.Hz / 16) * (p.Hz / 16) + (p.Hx / 16) * (p.Hx / 16);
+  const long long warps = static_cast<long long>(p.B) * Np + p.B;
+  patch_im2col_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(p);
+  return cudaGetLastError() != cudaSuccess;
+}
+inline int launch_im2col3x3(const Im2col3Params& p, cudaStream_t s) {
+  const long long warps = 9LL * p.G * p.B * p.S * p.S;
+  im2col3x3_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(p);
+  return cudaGetLastError() != cudaSuccess;
+}
+inline int launch_build_bias(const BiasParams& p, cudaStream_t s) {
+  const int total = p.B * (1 + p.Nz + p.Nx + p.T);
+  build_bias_kernel<<<(total + 255) / 256, 256, 0, s>>>(p);
+  return cudaGetLastError() != cudaSuccess;
 }
 
 }  // namespace uvlt

@@ -1,0 +1,73 @@
+"""Batch-of-sequences data parallelism across the GPUs of one node.
+
+The per-frame path shards over independent sequences only (the reference itself runs one
+process per GPU with no communication, lib/test/evaluation/running.py:97-100,170).  One process per GPU, rank r owns
+a contiguous block of sequences, there is no per-frame collective, and the run ends with ONE all-gather of the
+per-sequence trajectories [S_local, T, 4] -> [S_total, T, 4] on every rank (NCCL over NVLink on the B200 box, gloo in
+the CPU tests).
+"""
+from __future__ import annotations
+
+import os
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_range(n_sequences: int, rank: int, world: int):
+    """Contiguous, balanced block of sequence indices owned by `rank` (the first n % world ranks get one more)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_sequences, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def init_process_group(backend: str | None = None):
+    """Join the torchrun rendezvous (MASTER_ADDR/PORT, RANK, WORLD_SIZE from the environment)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = env_rank_world()
+    if world == 1:
+        return rank, world, local
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def gather_trajectories(local, n_sequences: int | None = None):
+    """All-gather per-rank trajectories [S_local, T, C] into [S_total, T, C] on every rank, in rank order.
+
+    Ranks may own different numbers of sequences (shard_range); blocks are padded to the largest shard for the
+    collective and trimmed afterwards.  With one process this is the identity."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    counts[dist.get_rank()] = local.shape[0]
+    dist.all_reduce(counts)
+    counts = counts.tolist()
+    smax = max(counts)
+    send = local.new_zeros((smax,) + tuple(local.shape[1:]))
+    send[: local.shape[0]] = local
+    recv = local.new_empty((world * smax,) + tuple(local.shape[1:]))
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(recv, send.contiguous())
+    else:
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send.contiguous())
+        recv = torch.cat(parts, dim=0)
+    out = torch.cat([recv[r * smax: r * smax + counts[r]] for r in range(world)], dim=0)
+    if n_sequences is not None and out.shape[0] != n_sequences:
+        raise RuntimeError(f"gathered {out.shape[0]} sequences, expected {n_sequences}")
+    return out

@@ -1,0 +1,293 @@
+"""Tracker call surface of the reference (lib/test/tracker/uvltrack.py) on the sm_100a engine.
+
+``get_tracker_class()`` returns :class:`UVLTrack` with the reference's ``__init__(params, dataset_name)`` /
+``initialize(image, info)`` / ``track(image, info=None) -> {"target_bbox": [x, y, w, h]}``.  It is a batch-of-one view of
+:class:`BatchTracker`, which advances B independent sequences per engine call (sequences never
+interact, so they shard across GPUs with no per-frame communication).
+
+Per frame the host does what the reference's host does (square crop + resize with OpenCV, box bookkeeping); the device
+does everything else in ONE library call: H2D of the raw uint8 crops, fused normalisation + patch embedding, the
+transformer, the box head, the Hanning-window merge / argmax / gather and the D2H of one [B, 6] row block
+(``uvlt_track_frame_host``).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import preprocess as pp
+from .misc import NestedTensor
+from .model import build_model
+
+
+class WordPieceTokenizer:
+    """Minimal BERT uncased tokenizer (what ``BertTokenizer.from_pretrained(vocab, do_lower_case=True)`` of
+    pytorch_pretrained_bert does for plain ASCII queries): lower-case, split on whitespace and punctuation, greedy
+    longest-match-first WordPiece with '##' continuations, '[UNK]' for unmatched words."""
+
+    def __init__(self, vocab_path: str):
+        self.vocab = {}
+        with open(vocab_path, encoding="utf-8") as f:
+            for i, line in enumerate(f):
+                self.vocab[line.rstrip("\n")] = i
+        self.unk = "[UNK]"
+
+    @staticmethod
+    def _basic(text: str):
+        out, cur = [], ""
+        for ch in text.lower():
+            if ch.isspace():
+                if cur:
+                    out.append(cur)
+                    cur = ""
+            elif not ch.isalnum():
+                if cur:
+                    out.append(cur)
+                    cur = ""
+                out.append(ch)
+            else:
+                cur += ch
+        if cur:
+            out.append(cur)
+        return out
+
+    def tokenize(self, text: str):
+        toks = []
+        for word in self._basic(text):
+            if len(word) > 100:
+                toks.append(self.unk)
+                continue
+            start, sub, bad = 0, [], False
+            while start < len(word):
+                end, cur = len(word), None
+                while start < end:
+                    piece = ("##" if start > 0 else "") + word[start:end]
+                    if piece in self.vocab:
+                        cur = piece
+                        break
+                    end -= 1
+                if cur is None:
+                    bad = True
+                    break
+                sub.append(cur)
+                start = end
+            toks.extend([self.unk] if bad else sub)
+        return toks
+
+    def convert_tokens_to_ids(self, tokens):
+        return [self.vocab.get(t, self.vocab.get(self.unk, 100)) for t in tokens]
+
+
+def extract_token_from_nlp(tokenizer, nlp: str, seq_length: int):
+    """lib/test/tracker/uvltrack.py:196-233: [CLS] tokens [SEP], zero padded to seq_length; returns (ids, mask) lists."""
+    toks = tokenizer.tokenize(nlp)[: seq_length - 2]
+    ids = tokenizer.convert_tokens_to_ids(["[CLS]"] + toks + ["[SEP]"])
+    mask = [1] * len(ids)
+    pad = seq_length - len(ids)
+    return ids + [0] * pad, mask + [0] * pad
+
+
+class BatchTracker:
+    """B independent sequences advanced in lock step on one GPU."""
+
+    def __init__(self, params, batch: int = 1, network=None):
+        import torch
+
+        self.params = params
+        self.cfg = params.cfg
+        self.B = int(batch)
+        if network is None:
+            network = build_model(self.cfg, max_batch=self.B)
+            sd = getattr(params, "state_dict", None)
+            if sd is None:
+                ckpt = getattr(params, "checkpoint", None)
+                if not ckpt or not os.path.exists(ckpt):
+                    raise FileNotFoundError(f"checkpoint {ckpt!r} not found and params.state_dict not given")
+                sd = torch.load(ckpt, map_location="cpu")["net"]  # lib/test/tracker/uvltrack.py:24
+            network.load_state_dict(sd, strict=False)
+        self.network = network
+        self.engine = network.engine
+        self.dims = network.dims
+        if self.engine.max_batch < self.B:
+            raise ValueError("engine max_batch is smaller than the tracker batch")
+        self.map_size = params.search_size // 16
+        self.update_interval = self.cfg.TEST.UPDATE_INTERVAL
+        self.threshold = self.cfg.TEST.THRESHOLD
+        self.has_cont = self.cfg.TRAIN.CONT_WEIGHT > 0
+        self.max_query_len = self.cfg.MODEL.BACKBONE.LANGUAGE.BERT.MAX_QUERY_LEN
+        self.tokenizer = None
+        self.frame_id = 0
+        self.state = [None] * self.B
+        self.max_score = [0.0] * self.B
+        self.pred_box_net = [None] * self.B
+        d, dev = self.dims, "cuda"
+        self.window = pp.hanning_window(self.map_size)
+        self.window_dev = torch.from_numpy(self.window).to(dev)
+        self.template = torch.zeros(self.B, 3, d.template_size, d.template_size, device=dev)
+        self.ids = torch.zeros(self.B, d.text_len, dtype=torch.int64, device=dev)
+        self.text_mask = torch.zeros(self.B, d.text_len, device=dev)
+        self.flag = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.prompt = torch.zeros(self.B, 3, d.embed_dim, device=dev)
+        self.max_score_dev = torch.zeros(self.B, device=dev)
+        self.snapshot = torch.zeros(self.B, d.n_tokens, d.embed_dim, device=dev)
+        self.template_mask = torch.zeros(self.B, d.nz, dtype=torch.uint8, device=dev)
+        self.crops = torch.empty(self.B, d.search_size, d.search_size, 3, dtype=torch.uint8, pin_memory=True)
+        self.crops_np = self.crops.numpy()
+        self.out = torch.zeros(self.B, 6, dtype=torch.float32, pin_memory=True)
+        self.out_np = self.out.numpy()
+        self.skip_text = False
+
+    # ------------------------------------------------------------------------------------------------------
+    def _tokens_for(self, info):
+        if "text_ids" in info:  # pre-tokenised query (synthetic runs: no vocabulary file is available offline)
+            ids = list(info["text_ids"])
+            mask = list(info.get("text_mask", [1 if i != 0 else 0 for i in ids]))
+            pad = self.max_query_len - len(ids)
+            return ids + [0] * pad, mask + [0] * pad
+        if self.tokenizer is None:
+            vocab = self.cfg.MODEL.BACKBONE.LANGUAGE.VOCAB_PATH
+            if not vocab or not os.path.exists(vocab):
+                raise FileNotFoundError(f"BERT vocabulary {vocab!r} not found; pass info['text_ids'] instead")
+            self.tokenizer = WordPieceTokenizer(vocab)
+        return extract_token_from_nlp(self.tokenizer, info["language"], self.max_query_len)
+
+    def _grounding(self, image, ids, mask):
+        """Tracker.grounding (lib/test/tracker/uvltrack.py:45-62): box from language alone on the whole frame."""
+        import torch
+
+        d = self.dims
+        h, w = image.shape[:2]
+        ground = torch.from_numpy(pp.normalize_image(pp.grounding_resize(image, self.params.grounding_size))).cuda()
+        template = torch.zeros(1, 3, d.template_size, d.template_size, device="cuda")
+        tm = torch.zeros(1, d.nz, dtype=torch.uint8, device="cuda")
+        cm = torch.zeros(1, d.nx, dtype=torch.uint8, device="cuda")
+        text = NestedTensor(torch.tensor([ids]).cuda(), torch.tensor([mask]).cuda())
+        out = self.network.forward(template, ground, text, tm, cm, torch.tensor([[1]]).cuda())
+        cx, cy, bw, bh = (out["pred_boxes"][0, 0] * float(max(h, w))).tolist()
+        box = [cx - 0.5 * bw, cy - 0.5 * bh, bw, bh]
+        box[0] += min(0, (w - h) / 2)
+        box[1] += min(0, (h - w) / 2)
+        return box
+
+    def initialize(self, images, infos):
+        """lib/test/tracker/uvltrack.py:70-104 for every sequence of the batch."""
+        import torch
+
+        d, mode = self.dims, self.cfg.TEST.MODE
+        ctx = torch.zeros(self.B, 3, d.search_size, d.search_size)
+        tmpl = torch.zeros(self.B, 3, d.template_size, d.template_size)
+        ctx_mask = np.zeros((self.B, d.nx), dtype=np.uint8)
+        tm_mask = np.zeros((self.B, d.nz), dtype=np.uint8)
+        ids_all = np.zeros((self.B, d.text_len), dtype=np.int64)
+        mask_all = np.zeros((self.B, d.text_len), dtype=np.float32)
+        flags = np.zeros(self.B, dtype=np.int64)
+        for b, (image, info) in enumerate(zip(images, infos)):
+            if mode == "NL":
+                ids, mask = self._tokens_for(info)
+                init_bbox = self._grounding(image, ids, mask)
+                flags[b] = 2
+            elif mode == "NLBBOX":
+                ids, mask = self._tokens_for(info)
+                init_bbox = list(info["init_bbox"])
+                flags[b] = 2
+            else:
+                ids, mask = [0] * d.text_len, [0] * d.text_len
+                init_bbox = list(info["init_bbox"])
+                flags[b] = 0
+            ids_all[b], mask_all[b] = ids, mask
+            z_patch, _, z_box = pp.sample_target(image, init_bbox, self.params.template_factor, self.params.template_size)
+            tm_mask[b] = pp.anno2mask(z_box.reshape(1, 4), d.template_size // 16)[0]
+            tmpl[b] = torch.from_numpy(pp.normalize_image(z_patch))[0]
+            y_patch, _, y_box = pp.sample_target(image, init_bbox, self.params.search_factor, self.params.search_size)
+            ctx[b] = torch.from_numpy(pp.normalize_image(y_patch))[0]
+            ctx_mask[b] = pp.anno2mask(y_box.reshape(1, 4), d.search_size // 16)[0]
+            self.state[b] = init_bbox
+            self.max_score[b] = 0.0
+            self.pred_box_net[b] = None
+        self.template.copy_(tmpl)
+        self.ids.copy_(torch.from_numpy(ids_all))
+        self.text_mask.copy_(torch.from_numpy(mask_all))
+        self.flag.copy_(torch.from_numpy(flags))
+        self.template_mask.copy_(torch.from_numpy(tm_mask))
+        self.max_score_dev.zero_()
+        self.skip_text = bool((flags == 0).all())
+        text = NestedTensor(self.ids, self.text_mask)
+        self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx.cuda(), text, self.template_mask,
+                                                           torch.from_numpy(ctx_mask).cuda(), self.flag))
+        self.frame_id = 0
+        torch.cuda.synchronize()
+
+    def track(self, images):
+        """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch."""
+        import torch
+
+        self.frame_id += 1
+        S = self.params.search_size
+        rf = [0.0] * self.B
+        for b, image in enumerate(images):
+            crop, rf[b], _ = pp.sample_target(image, self.state[b], self.params.search_factor, S)
+            self.crops_np[b] = crop
+        self.engine.track_frame_host(self.crops, self.template, self.ids, self.text_mask, self.prompt, self.flag,
+                                     self.window_dev, self.out, self.B, has_cont=self.has_cont,
+                                     skip_text=self.skip_text, max_score=self.max_score_dev, snapshot=self.snapshot)
+        results, update = [], []
+        for b, image in enumerate(images):
+            H, W = image.shape[:2]
+            row = self.out_np[b]
+            pred_box_net = row[:4].copy()
+            score = float(row[4])
+            pred_box = (pred_box_net * np.float32(S) / np.float32(rf[b])).tolist()
+            self.state[b] = pp.clip_box(pp.map_box_back(self.state[b], pred_box, rf[b], S), H, W, margin=10)
+            if score > self.max_score[b] and self.has_cont:
+                self.pred_box_net[b] = pred_box_net
+                self.max_score[b] = score
+            if self.frame_id % self.update_interval == 0 and self.has_cont and self.max_score[b] > self.threshold:
+                update.append(b)
+            results.append({"target_bbox": self.state[b], "score": score})
+        if update:
+            cm = np.zeros((self.B, self.dims.nx), dtype=np.uint8)
+            for b in update:
+                cx, cy, w, h = self.pred_box_net[b]
+                cm[b] = pp.anno2mask(np.array([[cx - 0.5 * w, cy - 0.5 * h, w, h]], dtype=np.float32), S // 16)[0]
+            new_prompt = self.engine.forward_prompt(self.snapshot, self.flag, self.template_mask,
+                                                    torch.from_numpy(cm).cuda(), self.text_mask)
+            sel = torch.tensor(update, device="cuda")
+            self.prompt[sel] = new_prompt[sel]
+            self.max_score_dev[sel] = 0
+            for b in update:
+                self.max_score[b] = 0.0
+        return results
+
+
+class UVLTrack:
+    """Reference call surface (lib/test/tracker/uvltrack.py:20-140), one sequence per object."""
+
+    def __init__(self, params, dataset_name=None, network=None):
+        self.params = params
+        self.cfg = params.cfg
+        self._bt = BatchTracker(params, batch=1, network=network)
+        self.network = self._bt.network
+        self.debug = getattr(params, "debug", 0)
+
+    @property
+    def state(self):
+        return self._bt.state[0]
+
+    @property
+    def frame_id(self):
+        return self._bt.frame_id
+
+    @property
+    def prompt(self):
+        return self._bt.prompt
+
+    def initialize(self, image, info: dict):
+        self._bt.initialize([image], [info])
+
+    def track(self, image, info: dict = None):
+        return {"target_bbox": self._bt.track([image])[0]["target_bbox"]}
+
+
+def get_tracker_class():
+    return UVLTrack

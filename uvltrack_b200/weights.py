@@ -71,11 +71,11 @@ class ModelDims:
 
     @staticmethod
     def large(template_size=128, search_size=256) -> "ModelDims":
-        # experiments/uvltrack/baseline_large.yaml: HIDDEN_DIM 1024, FUSION_LAYER 12..23, CONT_LOSS_LAYER 6..23 step?
+        # experiments/uvltrack/baseline_large.yaml:73-76,89: HIDDEN_DIM 1024, FUSION_LAYER 12..23, CONT_LOSS_LAYER 8..23
         return ModelDims(arch="large", embed_dim=1024, num_heads=16, depth=24, mlp_hidden=4096,
                          template_size=template_size, search_size=search_size,
                          fusion_layers=list(range(12, 24)),
-                         cont_loss_layers=list(range(6, 24)))
+                         cont_loss_layers=list(range(8, 24)))
 
     @staticmethod
     def from_cfg(cfg) -> "ModelDims":
@@ -128,7 +128,7 @@ def sincos_pos_embed(dim: int, grid_size: int) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def synthetic_state_dict(dims: ModelDims, seed: int = 0, cls_sharpen: float = 40.0) -> "OrderedDict[str, np.ndarray]":
+def synthetic_state_dict(dims: ModelDims, seed: int = 0, cls_sharpen: float = 4.0) -> "OrderedDict[str, np.ndarray]":
     """Reference-format ``state_dict`` (fp32 numpy) for every parameter/buffer reachable from the hot path."""
     rng = np.random.default_rng(seed)
     D, Hd = dims.embed_dim, dims.mlp_hidden
