@@ -254,7 +254,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
 
-    from tests.util import synthetic_sequence
+    from uvltrack_b200.synthetic import synthetic_sequence
     from uvltrack_b200 import NestedTensor, config, dp
     from uvltrack_b200.tracker import BatchTracker
     from uvltrack_b200.weights import ModelDims, synthetic_inputs, synthetic_state_dict

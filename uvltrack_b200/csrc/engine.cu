@@ -624,7 +624,6 @@ int run_head(uvlt_engine* e, Plan* p, cudaStream_t s, bool train_branch) {
   decode_kernel<<<B, 256, 0, s>>>(dp);
   if (cudaGetLastError() != cudaSuccess) { set_error("decode launch failed"); return 1; }
   ++e->launch_count;
-  e->last_cont_cols = (e->cfg.softmax_one && !train_branch) ? 3 : 2;
   return 0;
 }
 
@@ -873,6 +872,7 @@ int uvlt_forward_test(uvlt_handle e, const float* tmpl, const float* search, con
     return 1;
   if (run_core(e, p, s, logits, true)) return 1;
   e->last_B = B;
+  e->last_cont_cols = e->cfg.softmax_one ? 3 : 2;  // set here, not in run_head: a graph replay never re-runs the host code
   fill_outputs(e, B, out, logits);
   return 0;
 }
@@ -917,6 +917,7 @@ int uvlt_forward_train(uvlt_handle e, const float* tmpl, const float* search, co
   if (run_prompter(e, p, s, e->x, e->flag_d, e->mask_d, template_mask, context_mask, B / 2, e->prompt_d)) return 1;
   if (run_head(e, p, s, true)) return 1;
   e->last_B = B;
+  e->last_cont_cols = 2;
   fill_outputs(e, B, out, logits);
   return 0;
 }
@@ -966,6 +967,7 @@ int uvlt_track_frame_host(uvlt_handle e, const uint8_t* search_u8_host, const fl
     return 1;
   if (run_core(e, p, s, false, true)) return 1;
   e->last_B = B;
+  e->last_cont_cols = e->cfg.softmax_one ? 3 : 2;
   if (track_decode(e, s, B, window, has_cont, max_score, snapshot, e->track_out)) return 1;
   ENG_CUDA(cudaMemcpyAsync(out_host, e->track_out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
   ENG_CUDA(cudaStreamSynchronize(s));
