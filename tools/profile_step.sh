@@ -1,0 +1,18 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): launch list + full ncu captures of the dominant kernels of one bench step.
+#   tools/profile_step.sh <tag> [bench args...]
+# Outputs under gpurun_out/: <tag>_launches.csv, <tag>_gemm.ncu-rep, <tag>_attn.ncu-rep
+set -u
+TAG=$1; shift
+mkdir -p gpurun_out
+NCU="ncu --clock-control none"
+# every kernel of 2 timed steps (after warm-up launches are skipped by bench's own warm-up: we keep them all and filter here)
+timeout 600 $NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_launches.log 2>&1
+echo "launch list rc=$?"
+timeout 600 $NCU --set full --import-source on -k regex:gemm_bf16 -s 200 -c 4 -f -o gpurun_out/${TAG}_gemm \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_gemm.log 2>&1
+echo "gemm capture rc=$?"
+timeout 600 $NCU --set full --import-source on -k regex:attention_kernel -s 40 -c 2 -f -o gpurun_out/${TAG}_attn \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_attn.log 2>&1
+echo "attn capture rc=$?"
