@@ -77,7 +77,8 @@ UVLT_API int uvlt_set_weight(uvlt_handle h, const char* key, const float* data, 
  * (lib/models/heads/utils.py:126-130).  Fails if a required tensor was never set.  Synchronises the device. */
 UVLT_API int uvlt_finalize_weights(uvlt_handle h);
 
-/* options: "graph" (1: replay the layer chain as a CUDA graph, default 1), "bn" (force GEMM tile width, 0 = auto) */
+/* options: "graph" (1: replay the layer chain as a CUDA graph, default 1), "bn" (force GEMM tile width, 0 = auto),
+ * "pdl" (1: programmatic dependent launch between the kernels of the chain, default 1; process-wide) */
 UVLT_API int uvlt_set_option(uvlt_handle h, const char* name, int32_t value);
 
 typedef struct uvlt_outputs {
@@ -165,7 +166,7 @@ UVLT_API int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bia
                          int act, long long out_ld, long long out_gstride, int bn, void* stream);
 
 /* Fused MHA on packed qkv bf16 [B, n, 3*H*64] -> out bf16 [B, n, H*64]; key_bias fp32 [B, n] or NULL.
- * (block.py:47-58, bert_backbone.py:299-325).  v_t != NULL selects the bring-up variant with V^T [B,H*64,n_pad]. */
+ * (block.py:47-58, bert_backbone.py:299-325).  v_t / n_pad are reserved (pass NULL / 0). */
 UVLT_API int uvlt_op_attention(const void* qkv, const float* key_bias, void* out, int B, int n, int H, const void* v_t,
                       int n_pad, void* stream);
 

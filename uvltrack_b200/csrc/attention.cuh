@@ -10,10 +10,17 @@
 //   warp 1      MMA issuer   : S_j = Q K_j^T   (tcgen05, M=128, N<=128, K=64)  -> TMEM cols [0,128)
 //                              O  += P_j V_j   (tcgen05, M=128, N=64,  K<=128) -> TMEM cols [128,192)
 //                              V is consumed straight from its [key][64] tile as an MN-major B operand.
-//   warps 2..5  softmax      : thread = query row; tcgen05.ld S, online softmax in the exp2 domain (fp32 stats),
-//                              P_j -> bf16 -> swizzled smem (A operand of the PV MMA), rescale O in TMEM when the
-//                              running max moves, final O / l -> bf16 -> HBM.
-// 256 TMEM columns and ~100 KB smem per CTA -> two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
+//   warps 2..5  softmax      : thread = query row; online softmax in the exp2 domain with fp32 statistics.  TMEM reads
+//                              run at 64 B/cycle/SM, so an unmasked full block reads S ONCE (tcgen05.ld, software
+//                              pipelined 32 columns at a time): P = 2^(s*scale - ref) against the running reference
+//                              (one FFMA + one MUFU.EX2 + one FADD per score), the block maximum is tracked on the side
+//                              with 3-input max and only moves the reference of LATER blocks, and only when it grew by
+//                              more than 2^8; O / l are rescaled in TMEM when (rarely) the reference moves.  The exact
+//                              result is unchanged: P, l and O share the reference and O / l cancels it.  Masked or
+//                              partial blocks take a two-pass path with per-key bias.  P_j -> bf16 -> swizzled smem
+//                              (A operand of the PV MMA).
+// 112.25 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM: one CTA's softmax (MUFU bound: 16384
+// exp2 per 128x128 tile = 1024 cycles per SM) overlaps the other's MMAs (512 tensor cycles per tile at head dim 64).
 #pragma once
 #include "common.cuh"
 
@@ -24,7 +31,7 @@ constexpr int ATT_BKV = 128;   // keys per block
 constexpr int ATT_D = 64;      // head dim (both UVLTrack-B and -L)
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_STAGES = 2;
-constexpr int ATT_MAX_KV = 1280;  // bias staging (n <= 1193 at 384^2/384^2)
+constexpr int ATT_MAX_KV = 4096;  // 32 key blocks (bit mask of biased blocks)
 
 struct AttnParams {
   int n;               // sequence length (queries == keys)
@@ -42,23 +49,96 @@ struct AttnSmem {
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + ATT_STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + ATT_STAGES * KV_BYTES;
-  static constexpr int OFF_BIAS = OFF_P + P_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + ATT_MAX_KV * 4;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;  // 114944 B: 2 x (TOTAL + 1 KB reserved) <= 228 KB per SM
 };
 
-// V_KMAJOR = true is a bring-up alternative: V^T supplied as its own tensor [B, H, 64, n_pad] (keys contiguous).
-template <bool V_KMAJOR>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_vt,
-                 const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+constexpr float ATT_LOG2E = 1.4426950408889634f;
+
+// MODE 0: full unbiased block (fast path)   MODE 1: partial block, no bias   MODE 2: biased (and possibly partial)
+// maximum of the (biased, log2-scaled) scores of one 32-column chunk
+template <int MODE>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float scale, const float* bias_c, int lim) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (MODE == 0) {
+    // raw maximum; the positive scale is applied once afterwards
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    }
+    return fmaxf(m0, m1) * scale;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    // columns >= lim were never written by the MMA (stale TMEM) or belong to keys >= n
+    float x = __uint_as_float(v[i]) * scale;
+    if (MODE == 2) x = fmaf(__uint_as_float(v[i]), scale, (i < lim ? __ldg(bias_c + i) : 0.0f) * ATT_LOG2E);
+    m0 = fmaxf(m0, i < lim ? x : -INFINITY);
+  }
+  return m0;
+}
+
+// probabilities of one 32-column chunk -> bf16 pairs; returns the fp32 row-sum contribution
+template <int MODE>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], float scale, float neg_m,
+                                           const float* bias_c, int lim) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0, p1;
+    if (MODE == 2) {
+      const float b0 = (i < lim ? __ldg(bias_c + i) : 0.0f) * ATT_LOG2E;
+      const float b1 = (i + 1 < lim ? __ldg(bias_c + i + 1) : 0.0f) * ATT_LOG2E;
+      p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale, b0) + neg_m);
+      p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale, b1) + neg_m);
+    } else {
+      p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale, neg_m));
+      p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale, neg_m));
+    }
+    if (MODE != 0) {
+      p0 = i < lim ? p0 : 0.0f;  // stale TMEM columns past the last real key must not reach P
+      p1 = i + 1 < lim ? p1 : 0.0f;
+    }
+    s0 += p0;
+    s1 += p1;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  return s0 + s1;
+}
+
+__device__ __forceinline__ float chunk_max_dyn(int mode, const uint32_t (&v)[32], float scale, const float* bias_c,
+                                               int lim) {
+  if (mode == 0) return chunk_max<0>(v, scale, nullptr, 32);
+  if (mode == 1) return chunk_max<1>(v, scale, nullptr, lim);
+  return chunk_max<2>(v, scale, bias_c, lim);
+}
+__device__ __forceinline__ float chunk_exp_dyn(int mode, const uint32_t (&v)[32], uint32_t (&pk)[16], float scale,
+                                               float neg_m, const float* bias_c, int lim) {
+  if (mode == 0) return chunk_exp<0>(v, pk, scale, neg_m, nullptr, 32);
+  if (mode == 1) return chunk_exp<1>(v, pk, scale, neg_m, nullptr, lim);
+  return chunk_exp<2>(v, pk, scale, neg_m, bias_c, lim);
+}
+
+static __global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t att_smem[];  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
+  uint8_t* const smem = att_smem;
   uint8_t* sQ = smem + AttnSmem::OFF_Q;
   uint8_t* sK = smem + AttnSmem::OFF_K;
   uint8_t* sV = smem + AttnSmem::OFF_V;
   uint8_t* sP = smem + AttnSmem::OFF_P;
-  float* sBias = reinterpret_cast<float*>(smem + AttnSmem::OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]
@@ -78,8 +158,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
   const int nblk = (p.n + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("uvlt: attention dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tma_qkv);
-    if (V_KMAJOR) tma_prefetch_desc(&tma_vt);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -95,18 +178,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  // stage the key bias (pre-multiplied by log2 e); keys >= n get -inf so padded columns vanish
-  for (int i = threadIdx.x; i < nblk * ATT_BKV; i += ATT_THREADS) {
-    float v = -INFINITY;
-    if (i < p.n) v = p.bias ? p.bias[static_cast<long long>(b) * p.n + i] * 1.4426950408889634f : 0.0f;
-    sBias[i] = v;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + ATT_BKV;
+  pdl_wait();  // bias and qkv come from earlier kernels of the chain
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -119,14 +198,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * AttnSmem::KV_BYTES);
         tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_qkv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
-        if (V_KMAJOR) {
-          // V^T tile [64 d rows x 128 keys] as two 64-key halves (128 B swizzle atoms)
-          tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_vt, &kv_full[s], j * ATT_BKV, h * ATT_D, b);
-          tma_load_3d(sV + s * AttnSmem::KV_BYTES + AttnSmem::KV_BYTES / 2, &tma_vt, &kv_full[s],
-                      j * ATT_BKV + 64, h * ATT_D, b);
-        } else {
-          tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_qkv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
-        }
+        tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_qkv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
       }
     }
   } else if (warp == 1) {
@@ -150,7 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
       for (int j = 0; j < nblk; ++j) {
         const int s = j % ATT_STAGES;
         if (j + 1 < nblk) {
-          // S_j has been consumed by the softmax warps -> overwrite with S_{j+1} while they work on P_j
+          // S_j has been consumed by the softmax warps -> overwrite with S_{j+1} while they finish P_j
           mbar_wait(s_empty, j & 1);
           mbar_wait(&kv_full[(j + 1) % ATT_STAGES], ((j + 1) / ATT_STAGES) & 1);
           tc_fence_after();
@@ -160,23 +232,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         tc_fence_after();
         const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
         const int ksteps = (kv_valid + 15) >> 4;
-        constexpr uint32_t idesc_pv_mn = umma_idesc_bf16(ATT_BQ, ATT_D, 1);
-        constexpr uint32_t idesc_pv_k = umma_idesc_bf16(ATT_BQ, ATT_D, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 1);
         const uint32_t p_addr = smem_u32(sP);
         const uint32_t v_addr = smem_u32(sV + s * AttnSmem::KV_BYTES);
         for (int k = 0; k < ksteps; ++k) {
           // P: two [128 x 64] K-major halves; 16 keys = 32 B inside the swizzle atom
           const uint64_t adesc = umma_smem_desc_sw128(p_addr + (k >> 2) * (AttnSmem::P_BYTES / 2), 1024, 0) + 2 * (k & 3);
-          uint64_t bdesc;
-          if (V_KMAJOR) {
-            // V^T halves: [64 d rows x 64 keys] K-major
-            bdesc = umma_smem_desc_sw128(v_addr + (k >> 2) * (AttnSmem::KV_BYTES / 2), 1024, 0) + 2 * (k & 3);
-            umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv_k, (j > 0 || k > 0) ? 1u : 0u);
-          } else {
-            // V: [key][64] rows of 128 B = MN-major B operand; 16 keys = 16 rows = 2048 B
-            bdesc = umma_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
-            umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv_mn, (j > 0 || k > 0) ? 1u : 0u);
-          }
+          // V: [key][64] rows of 128 B = MN-major B operand; 16 keys = 16 rows = 2048 B
+          const uint64_t bdesc = umma_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
+          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&kv_empty[s]);
         umma_commit(pv_done);
@@ -187,63 +251,121 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(lane_grp * 32) << 16;
-    float m_run = -INFINITY;
+    const float scale = p.scale_log2;
+    // which key blocks carry a non-zero bias (warp-uniform bit mask); all other full blocks take the fast path
+    uint32_t biased = 0;
+    if (p.bias) {
+      const float* bb = p.bias + static_cast<long long>(b) * p.n;
+      for (int j = 0; j < nblk; ++j) {
+        bool nz = false;
+        for (int i = lane; i < ATT_BKV; i += 32) {
+          const int k = j * ATT_BKV + i;
+          nz |= (k < p.n) && (__ldg(bb + k) != 0.0f);
+        }
+        if (__any_sync(0xffffffffu, nz)) biased |= 1u << j;
+      }
+    }
+    float m_run = -INFINITY;  // reference wanted for the next block (scaled log2 domain): the largest score seen,
+                              // updated only when it grows by more than 2^8
+    float o_ref = -INFINITY;  // reference the TMEM output and l_run are currently expressed in
     float l_run = 0.0f;
+    uint8_t* const p_row = sP + row * 128;
+    auto store_p = [&](int c, const uint32_t (&pk)[16]) {
+      // 32 keys = four 16 B chunks of this row; chunk index inside the 64-key half is XOR-swizzled with row%8
+      uint8_t* half_base = p_row + (c >> 1) * (AttnSmem::P_BYTES / 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+        *reinterpret_cast<uint4*>(half_base + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      }
+    };
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
       const int nchunk = (kv_valid + 31) >> 5;
-      const float* bj = sBias + j * ATT_BKV;
+      const int mode = ((biased >> j) & 1u) ? 2 : (kv_valid < ATT_BKV ? 1 : 0);  // block-uniform
+      const float* bj = p.bias ? p.bias + static_cast<long long>(b) * p.n + j * ATT_BKV : nullptr;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: block maximum of the biased, log2-scaled scores
-      float m_blk = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_wait_ld();
-        const int lim = kv_valid - c * 32;  // columns >= lim were never written by the MMA (stale TMEM)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]);
-          m_blk = fmaxf(m_blk, i < lim ? x : -INFINITY);
-        }
-      }
-      const float m_new = fmaxf(m_run, m_blk);          // finite: every block has >= 1 real, unmasked-or-finite key
-      const float alpha = exp2f(m_run - m_new);          // 0 on the first block (m_run = -inf)
-      // P buffer (and O) are free once PV_{j-1} has drained
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-      tc_fence_after();
-      // pass 2: probabilities -> bf16 -> swizzled smem, row sum in fp32
+
+      float ref;            // exp reference of this block's P (per row)
+      float m_blk;          // this block's row maximum
       float l_blk = 0.0f;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_wait_ld();
-        uint32_t pk[16];
-        const int lim = kv_valid - c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, bj[c * 32 + i]) - m_new);
-          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, bj[c * 32 + i + 1]) - m_new);
-          p0 = i < lim ? p0 : 0.0f;       // stale TMEM columns past the last real key must not reach P
-          p1 = i + 1 < lim ? p1 : 0.0f;
-          l_blk += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+      bool two_pass = mode != 0;
+      uint32_t va[32], vb[32], pk[16];
+      if (!two_pass) {
+        // ---- single pass (TMEM reads are 64 B/cycle/SM: S is read once).  Reference = the running one; on the first
+        //      block the maximum of the first 32 keys.  P may exceed 1 by up to the growth of the maximum, which bf16 /
+        //      fp32 represent exactly as well; beyond 2^64 the block is redone with its own maximum. ----
+        tmem_ld32(tmem_S + lane_off, va);
+        tmem_wait_ld_dep(va);
+        const float c0 = chunk_max<0>(va, scale, nullptr, 32);
+        ref = (m_run == -INFINITY) ? c0 : m_run;
+        const float neg_ref = -ref;
+        float mx = c0;
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free once PV_{j-1} has drained
+        tmem_ld32(tmem_S + lane_off + 32, vb);
+        l_blk += chunk_exp<0>(va, pk, scale, neg_ref, nullptr, 32);
+        store_p(0, pk);
+        tmem_wait_ld_dep(vb);
+        tmem_ld32(tmem_S + lane_off + 64, va);
+        mx = fmaxf(mx, chunk_max<0>(vb, scale, nullptr, 32));
+        l_blk += chunk_exp<0>(vb, pk, scale, neg_ref, nullptr, 32);
+        store_p(1, pk);
+        tmem_wait_ld_dep(va);
+        tmem_ld32(tmem_S + lane_off + 96, vb);
+        mx = fmaxf(mx, chunk_max<0>(va, scale, nullptr, 32));
+        l_blk += chunk_exp<0>(va, pk, scale, neg_ref, nullptr, 32);
+        store_p(2, pk);
+        tmem_wait_ld_dep(vb);
+        mx = fmaxf(mx, chunk_max<0>(vb, scale, nullptr, 32));
+        l_blk += chunk_exp<0>(vb, pk, scale, neg_ref, nullptr, 32);
+        store_p(3, pk);
+        m_blk = mx;
+        two_pass = __any_sync(0xffffffffu, m_blk > ref + 64.0f);  // overflow guard (never seen in practice)
+      }
+      if (two_pass) {
+        // ---- pass 1: block maximum (loads of chunk c+1 in flight while chunk c is reduced) ----
+        m_blk = -INFINITY;
+        tmem_ld32(tmem_S + lane_off, va);
+        tmem_wait_ld_dep(va);
+        for (int c = 0; c < nchunk; c += 2) {
+          if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
+          m_blk = fmaxf(m_blk, chunk_max_dyn(mode, va, scale, bj + c * 32, kv_valid - c * 32));
+          tmem_wait_ld_dep(vb);
+          if (c + 1 < nchunk) {
+            if (c + 2 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 2) * 32, va);
+            m_blk = fmaxf(m_blk, chunk_max_dyn(mode, vb, scale, bj + (c + 1) * 32, kv_valid - (c + 1) * 32));
+            tmem_wait_ld_dep(va);
+          }
         }
-        // 32 keys = four 16 B chunks of this row; chunk index inside the 64-key half is XOR-swizzled with row%8
-        uint8_t* half_base = sP + (c >> 1) * (AttnSmem::P_BYTES / 2) + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-          *reinterpret_cast<uint4*>(half_base + chunk * 16) =
-              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        // keep the stale reference unless the maximum grew by more than 2^8 (P stays <= 256, exact after O / l)
+        ref = (m_blk > m_run + 8.0f) ? m_blk : m_run;  // m_run = -inf on the first block -> m_blk
+        const float neg_ref = -ref;
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+        // ---- pass 2: probabilities -> bf16 -> swizzled smem, fp32 row sum ----
+        l_blk = 0.0f;
+        tmem_ld32(tmem_S + lane_off, va);
+        tmem_wait_ld_dep(va);
+        for (int c = 0; c < nchunk; c += 2) {
+          if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
+          l_blk += chunk_exp_dyn(mode, va, pk, scale, neg_ref, bj + c * 32, kv_valid - c * 32);
+          store_p(c, pk);
+          tmem_wait_ld_dep(vb);
+          if (c + 1 < nchunk) {
+            if (c + 2 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 2) * 32, va);
+            l_blk += chunk_exp_dyn(mode, vb, pk, scale, neg_ref, bj + (c + 1) * 32, kv_valid - (c + 1) * 32);
+            store_p(c + 1, pk);
+            tmem_wait_ld_dep(va);
+          }
         }
       }
-      // a partially filled 16-key MMA step may read up to the next 32-key boundary: already covered (nchunk*32)
+      // a partially filled 16-key MMA step may read up to the next 32-key boundary: covered (nchunk * 32 written)
       tc_fence_before();
       mbar_arrive(s_empty);
-      // rescale the running output when the maximum moved (skipped warp-wide when nobody needs it)
-      if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+      // bring the running output / sum to this block's reference (skipped warp-wide when no row moved)
+      tc_fence_after();
+      const float alpha = (o_ref == ref) ? 1.0f : ex2_approx(o_ref - ref);  // 0 on the first block (o_ref = -inf)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
         for (int c = 0; c < ATT_D; c += 32) {
           uint32_t o[32];
@@ -256,7 +378,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         tmem_wait_st();
       }
       l_run = l_run * alpha + l_blk;
-      m_run = m_new;
+      o_ref = ref;
+      m_run = (m_blk > ref + 8.0f) ? m_blk : ref;
       fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);

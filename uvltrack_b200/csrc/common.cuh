@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace uvlt {
 
@@ -36,6 +37,41 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the per-frame chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident (barrier init, TMEM allocation,
+// tensor-map prefetch) while its predecessor is still running, and blocks in pdl_wait() until the predecessor grid has
+// completed and its writes are visible.  Rules: nothing produced by an earlier kernel is touched before pdl_wait(),
+// and every kernel calls pdl_wait() unconditionally so that completion stays transitive along the chain.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#define UVLT_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)::uvlt::launch_k(kernel, grid, block, smem, stream, __VA_ARGS__)
+
+// uvlt_set_option("pdl", 0/1); the environment variable UVLT_PDL=0 disables it for a whole process (A/B timing)
+inline int g_pdl_enabled = [] {
+  const char* e = getenv("UVLT_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -193,6 +229,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for the outstanding tcgen05.ld and tie the destination registers to the wait, so the compiler cannot move a
+// use of `r` above it when other work is scheduled between the load and the wait (software-pipelined loads).
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+        "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+        "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+        "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace uvlt

@@ -507,7 +507,7 @@ int backbone_logits(uvlt_engine* e, cudaStream_t s, int B, int slot) {
   p.n_layers = e->cfg.num_cont_layers;
   p.layer_slot = slot;
   dim3 grid((e->Nx + 7) / 8, B);
-  backbone_logits_kernel<<<grid, 256, 2 * e->D * sizeof(float), s>>>(p);
+  UVLT_LAUNCH(backbone_logits_kernel, dim3(grid), dim3(256), 2 * e->D * sizeof(float), s, p);
   if (cudaGetLastError() != cudaSuccess) { set_error("backbone_logits launch failed"); return 1; }
   return 0;
 }
@@ -615,13 +615,13 @@ int run_head(uvlt_engine* e, Plan* p, cudaStream_t s, bool train_branch) {
   hp.softmax_one = e->cfg.softmax_one; hp.train_branch = train_branch ? 1 : 0;
   hp.offset_sigmoid = e->cfg.offset_sigmoid; hp.S = S; hp.B = B;
   hp.cls_map = e->cls_map; hp.bbox_map = e->bbox_map; hp.cont_score = e->cont_score; hp.cont_prob = e->cont_prob;
-  head_final_kernel<<<(B * e->SS + 7) / 8, 256, 0, s>>>(hp);
+  UVLT_LAUNCH(head_final_kernel, dim3((B * e->SS + 7) / 8), dim3(256), 0, s, hp);
   if (cudaGetLastError() != cudaSuccess) { set_error("head_final launch failed"); return 1; }
   ++e->launch_count;
   DecodeParams dp{};
   dp.cls_map = e->cls_map; dp.cont_prob = e->cont_prob; dp.bbox_map = e->bbox_map; dp.window = nullptr;
   dp.SS = e->SS; dp.mode = 0; dp.out = e->pred_boxes;
-  decode_kernel<<<B, 256, 0, s>>>(dp);
+  UVLT_LAUNCH(decode_kernel, dim3(B), dim3(256), 0, s, dp);
   if (cudaGetLastError() != cudaSuccess) { set_error("decode launch failed"); return 1; }
   ++e->launch_count;
   return 0;
@@ -637,13 +637,13 @@ int run_prompter(uvlt_engine* e, Plan* p, cudaStream_t s, const float* tokens, c
   pp.txt_mean = e->cfg.txt_token_mean; pp.text_mask = text_mask; pp.logit_scale_exp = e->pr_scale;
   pp.query_embed = e->pr_query; pp.src = e->pr_src; pp.src0 = e->pr_src0; pp.src_bf16 = e->pr_src_bf;
   if (e->Nz + e->Nx > PROMPTER_MAX_N) { set_error("prompter: too many target rows"); return 1; }
-  prompter_pool_kernel<<<B, 256, prompter_smem_bytes(e->D, e->Nz + e->Nx), s>>>(pp);
+  UVLT_LAUNCH(prompter_pool_kernel, dim3(B), dim3(256), prompter_smem_bytes(e->D, e->Nz + e->Nx), s, pp);
   if (cudaGetLastError() != cudaSuccess) { set_error("prompter_pool launch failed"); return 1; }
   ++e->launch_count;
   RUN(gemm_launch(p->pr_fc1, s));
   RUN(gemm_launch(p->pr_fc2, s));
   const int per_seq = 3 * e->D;
-  prompt_select_kernel<<<(per_seq * B + 255) / 256, 256, 0, s>>>(e->pr_out, e->pr_src0, flag, out, per_seq, B);
+  UVLT_LAUNCH(prompt_select_kernel, dim3((per_seq * B + 255) / 256), dim3(256), 0, s, e->pr_out, e->pr_src0, flag, out, per_seq, B);
   if (cudaGetLastError() != cudaSuccess) { set_error("prompt_select launch failed"); return 1; }
   ++e->launch_count;
   return 0;
@@ -741,13 +741,13 @@ int track_decode(uvlt_engine* e, cudaStream_t s, int B, const double* window, in
   const bool snap = has_cont && max_score && snapshot;
   dp.max_score = snap ? max_score : nullptr;
   dp.snap_flag = snap ? e->snap_flag : nullptr;
-  decode_kernel<<<B, 256, 0, s>>>(dp);
+  UVLT_LAUNCH(decode_kernel, dim3(B), dim3(256), 0, s, dp);
   if (cudaGetLastError() != cudaSuccess) { set_error("track decode launch failed"); return 1; }
   ++e->launch_count;
   if (snap) {
     const long long per_seq4 = static_cast<long long>(e->N) * e->D / 4;
     dim3 grid(32, B);
-    snapshot_kernel<<<grid, 256, 0, s>>>(e->x, snapshot, e->snap_flag, per_seq4);
+    UVLT_LAUNCH(snapshot_kernel, dim3(grid), dim3(256), 0, s, e->x, snapshot, e->snap_flag, per_seq4);
     if (cudaGetLastError() != cudaSuccess) { set_error("snapshot launch failed"); return 1; }
     ++e->launch_count;
   }
@@ -844,7 +844,14 @@ int uvlt_set_option(uvlt_handle e, const char* name, int32_t value) {
   if (!e || !name) { set_error("uvlt_set_option: null argument"); return 1; }
   const std::string n(name);
   if (n == "graph") e->use_graph = value != 0;
-  else if (n == "bn") {
+  else if (n == "pdl") {
+    // programmatic dependent launch for every kernel of the chain (process-wide); captured graphs must be rebuilt
+    g_pdl_enabled = value != 0;
+    cudaDeviceSynchronize();
+    for (auto& kv : e->plans)
+      for (auto& g : kv.second->graph)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  } else if (n == "bn") {
     if (value != 0 && value != 32 && value != 64 && value != 128) { set_error("bn must be 0/32/64/128"); return 1; }
     e->force_bn = value;
     cudaDeviceSynchronize();

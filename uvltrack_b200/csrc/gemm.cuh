@@ -40,16 +40,25 @@ struct GemmEpilogue {
 
 struct GemmShape {
   int M, N, K;
+  int stages;  // depth of the smem operand ring (2..GEMM_MAX_STAGES), chosen on the host from the grid size
 };
+
+constexpr int GEMM_MAX_STAGES = 12;
 
 template <int BN>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // ~96 KB of operand ring -> two CTAs per SM
-  static constexpr int STAGES = (96 * 1024) / STAGE_BYTES > 8 ? 8 : (96 * 1024) / STAGE_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BAR_BYTES = 256;  // 2 * GEMM_MAX_STAGES + 1 mbarriers + the TMEM slot
+  // dynamic smem for a ring of `stages`: [<=1023 B align slack][ring, 1024-aligned][barriers]
+  static constexpr int total(int stages) { return stages * STAGE_BYTES + 1024 + BAR_BYTES; }
+  // throughput configuration: ~96 KB of ring -> two CTAs per SM, one CTA's epilogue overlaps the other's mainloop
+  static constexpr int STAGES_2CTA = (96 * 1024) / STAGE_BYTES > 8 ? 8 : (96 * 1024) / STAGE_BYTES;
+  // latency configuration (grid <= one CTA per SM): as much of K in flight as fits in 227 KB
+  static constexpr int STAGES_1CTA =
+      (224 * 1024 - 1024 - BAR_BYTES) / STAGE_BYTES > GEMM_MAX_STAGES ? GEMM_MAX_STAGES
+                                                                     : (224 * 1024 - 1024 - BAR_BYTES) / STAGE_BYTES;
 };
 
 template <int BN>
@@ -57,15 +66,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                     const GemmShape shape, const GemmEpilogue ep) {
   using S = GemmSmem<BN>;
-  constexpr int STAGES = S::STAGES;
+  const int STAGES = shape.stages;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* acc_bar = empty_bar + GEMM_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -93,28 +102,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();     // everything above overlapped the predecessor's tail; A / residual are only read below
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         tma_load_3d(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
         tma_load_3d(b_dst, &tma_w, &full_bar[s], kb * GEMM_BK, n0, g);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
@@ -127,6 +139,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           umma_bf16_ss(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have drained
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(acc_bar);  // accumulator complete
     }

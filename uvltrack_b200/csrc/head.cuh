@@ -35,6 +35,8 @@ struct HeadFinalParams {
 };
 
 static __global__ void __launch_bounds__(256) head_final_kernel(const HeadFinalParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SS = p.S * p.S;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -143,6 +145,8 @@ struct DecodeParams {
 };
 
 static __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x;
@@ -207,6 +211,8 @@ struct BackboneLogitParams {
 };
 
 static __global__ void __launch_bounds__(256) backbone_logits_kernel(const BackboneLogitParams p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float s_tok[];  // [2][D] : vis token, txt token of this batch element
   const int b = blockIdx.y;
   const float* vis = p.img + static_cast<long long>(b) * p.img_bstride;
@@ -259,6 +265,8 @@ static __global__ void __launch_bounds__(256) backbone_logits_kernel(const Backb
 // ----------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) snapshot_kernel(const float* __restrict__ x, float* __restrict__ snap,
                                                        const int* __restrict__ snap_flag, long long per_seq4) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   if (!snap_flag[b]) return;
   const float4* src = reinterpret_cast<const float4*>(x) + b * per_seq4;
@@ -336,6 +344,8 @@ __device__ __forceinline__ void masked_softmax(const float* sim, int n, float* o
 constexpr int PROMPTER_MAX_N = 2048;  // Nz + Nx <= 2048 (384^2 + 384^2 -> 1152)
 
 static __global__ void __launch_bounds__(256) prompter_pool_kernel(const PrompterParams p) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int n = p.Nz + p.Nx;
   float* tok = sm;                       // [D]
@@ -467,6 +477,8 @@ inline size_t prompter_smem_bytes(int D, int n) {
 // switcher of heads/utils.py:93-97: [src, src_, src][flag]
 static __global__ void __launch_bounds__(256) prompt_select_kernel(const float* mlp_out, const float* src0,
                                                             const long long* flag, float* out, int per_seq, int B) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_seq * B) return;
   const int b = i / per_seq;

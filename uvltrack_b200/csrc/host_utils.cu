@@ -2,6 +2,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <mutex>
 
 namespace uvlt {
@@ -56,27 +57,28 @@ int init_kernel_attributes() {
   std::lock_guard<std::mutex> lk(mu);
   if (status == 0) return 0;
   UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<32>::TOTAL));
+                                    GemmSmem<32>::total(GemmSmem<32>::STAGES_1CTA)));
   UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<64>::TOTAL));
+                                    GemmSmem<64>::total(GemmSmem<64>::STAGES_1CTA)));
   UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<128>::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    AttnSmem::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    AttnSmem::TOTAL));
+                                    GemmSmem<128>::total(GemmSmem<128>::STAGES_1CTA)));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
   status = 0;
   return 0;
 }
 
 int pick_bn(int M, int N, int groups) {
+  // Widest tile that still gives >= 90 CTAs (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
+  // which bounds these launches, until fewer than ~2/3 of the SMs have work); below that, the narrowest legal tile.
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int cands[3] = {128, 64, 32};
   int best = 0;
   for (int bn : cands) {
     if (N % bn) continue;
     best = bn;
-    if (static_cast<long long>(m_tiles) * (N / bn) * groups >= 2 * 148) break;  // >= one full wave at 2 CTAs/SM
+    if (static_cast<long long>(m_tiles) * (N / bn) * groups >= 90) break;
   }
   return best;
 }
@@ -93,7 +95,17 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
               " K=" + std::to_string(K) + ")");
     return 1;
   }
-  g->shape = GemmShape{M, N, K};
+  g->shape = GemmShape{M, N, K, 0};
+  {
+    // ring depth: a grid that fits one CTA per SM is latency bound -> put as much of K in flight as shared memory
+    // allows; larger grids keep ~96 KB rings so two CTAs share an SM and overlap epilogue with mainloop
+    const long long tiles = static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / bn) * groups;
+    const int s1 = bn == 32 ? GemmSmem<32>::STAGES_1CTA : bn == 64 ? GemmSmem<64>::STAGES_1CTA : GemmSmem<128>::STAGES_1CTA;
+    const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA : GemmSmem<128>::STAGES_2CTA;
+    int st = tiles <= 148 ? s1 : s2;
+    st = std::min(st, K / GEMM_BK);
+    g->shape.stages = std::max(st, 1);
+  }
   g->ep = ep;
   g->bn = bn;
   g->groups = groups;
@@ -107,13 +119,13 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups);
   switch (g.bn) {
     case 32:
-      gemm_bf16_tn_kernel<32><<<grid, GEMM_THREADS, GemmSmem<32>::TOTAL, stream>>>(g.tma_a, g.tma_w, g.shape, g.ep);
+      UVLT_LAUNCH(gemm_bf16_tn_kernel<32>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<32>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
       break;
     case 64:
-      gemm_bf16_tn_kernel<64><<<grid, GEMM_THREADS, GemmSmem<64>::TOTAL, stream>>>(g.tma_a, g.tma_w, g.shape, g.ep);
+      UVLT_LAUNCH(gemm_bf16_tn_kernel<64>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<64>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
       break;
     default:
-      gemm_bf16_tn_kernel<128><<<grid, GEMM_THREADS, GemmSmem<128>::TOTAL, stream>>>(g.tma_a, g.tma_w, g.shape, g.ep);
+      UVLT_LAUNCH(gemm_bf16_tn_kernel<128>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<128>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
       break;
   }
   UVLT_CUDA_OK(cudaGetLastError());
@@ -122,6 +134,11 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
 
 int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
                  int n_pad) {
+  (void)n_pad;
+  if (vt) {
+    set_error("attention: the separate V^T operand of the bring-up kernel is no longer supported (pass NULL)");
+    return 1;
+  }
   if (n > ATT_MAX_KV || n <= 0) {
     set_error("attention: sequence length out of range");
     return 1;
@@ -129,14 +146,6 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   const long long D3 = 3LL * H * ATT_D;
   // [B, n, 3D]: rows >= n are out of bounds inside each batch element -> TMA zero fill (no cross-sequence reads)
   if (make_tma_bf16_3d(&a->tma_qkv, qkv, D3, n, B, D3 * 2, static_cast<uint64_t>(n) * D3 * 2, ATT_BQ)) return 1;
-  a->v_kmajor = vt != nullptr;
-  if (vt) {
-    if (make_tma_bf16_3d(&a->tma_vt, vt, n_pad, static_cast<uint64_t>(H) * ATT_D, B, static_cast<uint64_t>(n_pad) * 2,
-                         static_cast<uint64_t>(H) * ATT_D * n_pad * 2, 64))
-      return 1;
-  } else {
-    a->tma_vt = a->tma_qkv;
-  }
   a->p.n = n;
   a->p.H = H;
   a->p.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim 64
@@ -148,10 +157,7 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
-  if (a.v_kmajor)
-    attention_kernel<true><<<grid, ATT_THREADS, AttnSmem::TOTAL, stream>>>(a.tma_qkv, a.tma_vt, a.p);
-  else
-    attention_kernel<false><<<grid, ATT_THREADS, AttnSmem::TOTAL, stream>>>(a.tma_qkv, a.tma_vt, a.p);
+  UVLT_LAUNCH(attention_kernel, grid, dim3(ATT_THREADS), AttnSmem::TOTAL, stream, a.tma_qkv, a.p);
   UVLT_CUDA_OK(cudaGetLastError());
   return 0;
 }

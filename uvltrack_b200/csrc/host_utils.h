@@ -45,10 +45,9 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int pick_bn(int M, int N, int groups);
 
 struct AttnLaunch {
-  CUtensorMap tma_qkv, tma_vt;
+  CUtensorMap tma_qkv;
   AttnParams p;
   int B;
-  bool v_kmajor;
 };
 int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
                  int n_pad);

@@ -30,6 +30,8 @@ struct LnParams {
 
 template <int NV>  // D = NV * 128  (768 -> 6, 1024 -> 8)
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -101,6 +103,8 @@ struct BertEmbedParams {
 
 template <int NV>
 __global__ void __launch_bounds__(256) bert_embed_kernel(const BertEmbedParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -172,6 +176,8 @@ struct PatchParams {
 };
 
 static __global__ void __launch_bounds__(256) patch_im2col_kernel(const PatchParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int gz = p.Hz >> 4, gx = p.Hx >> 4;
   const int Nz = gz * gz, Nx = gx * gx;
   const int rows = p.B * (Nz + Nx);
@@ -255,6 +261,8 @@ struct Im2col3Params {
 };
 
 static __global__ void __launch_bounds__(256) im2col3x3_kernel(const Im2col3Params p) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long wg = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int SS = p.S * p.S;
@@ -310,6 +318,8 @@ struct BiasParams {
 };
 
 static __global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int Nv = 1 + p.Nz + p.Nx, N = Nv + p.T;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (p.prompt) {
@@ -339,32 +349,32 @@ static __global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams
 // ----------------------------------------------------------------------------------------------
 inline int launch_layernorm(const LnParams& p, int D, cudaStream_t s) {
   const int blocks = (p.total_rows + 7) / 8;
-  if (D == 768) layernorm_kernel<6><<<blocks, 256, 0, s>>>(p);
-  else if (D == 1024) layernorm_kernel<8><<<blocks, 256, 0, s>>>(p);
+  if (D == 768) UVLT_LAUNCH(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, p);
+  else if (D == 1024) UVLT_LAUNCH(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, s, p);
   else return 1;
   return cudaGetLastError() != cudaSuccess;
 }
 inline int launch_bert_embed(const BertEmbedParams& p, int D, cudaStream_t s) {
   const int blocks = (p.total_rows + 7) / 8;
-  if (D == 768) bert_embed_kernel<6><<<blocks, 256, 0, s>>>(p);
-  else if (D == 1024) bert_embed_kernel<8><<<blocks, 256, 0, s>>>(p);
+  if (D == 768) UVLT_LAUNCH(bert_embed_kernel<6>, dim3(blocks), dim3(256), 0, s, p);
+  else if (D == 1024) UVLT_LAUNCH(bert_embed_kernel<8>, dim3(blocks), dim3(256), 0, s, p);
   else return 1;
   return cudaGetLastError() != cudaSuccess;
 }
 inline int launch_patch_im2col(const PatchParams& p, cudaStream_t s) {
   const int Np = (p.Hz / 16) * (p.Hz / 16) + (p.Hx / 16) * (p.Hx / 16);
   const long long warps = static_cast<long long>(p.B) * Np + p.B;
-  patch_im2col_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(p);
+  UVLT_LAUNCH(patch_im2col_kernel, dim3(static_cast<unsigned>((warps + 7) / 8)), dim3(256), 0, s, p);
   return cudaGetLastError() != cudaSuccess;
 }
 inline int launch_im2col3x3(const Im2col3Params& p, cudaStream_t s) {
   const long long warps = 9LL * p.G * p.B * p.S * p.S;
-  im2col3x3_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, s>>>(p);
+  UVLT_LAUNCH(im2col3x3_kernel, dim3(static_cast<unsigned>((warps + 7) / 8)), dim3(256), 0, s, p);
   return cudaGetLastError() != cudaSuccess;
 }
 inline int launch_build_bias(const BiasParams& p, cudaStream_t s) {
   const int total = p.B * (1 + p.Nz + p.Nx + p.T);
-  build_bias_kernel<<<(total + 255) / 256, 256, 0, s>>>(p);
+  UVLT_LAUNCH(build_bias_kernel, dim3((total + 255) / 256), dim3(256), 0, s, p);
   return cudaGetLastError() != cudaSuccess;
 }
 
