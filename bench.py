@@ -9,8 +9,8 @@
 
 A "step" is one tracker frame for every sequence of the per-GPU batch.  One JSON line is printed by rank 0:
   value     frames/s (all GPUs) of forward_test + window merge/argmax with inputs resident in HBM (CUDA events)
-  e2e       frames/s through the reference-facing call surface Tracker.track(): host crop (OpenCV), H2D of the uint8
-            crops from pinned memory, the engine, D2H of the [B,6] result rows, host box bookkeeping, prompt updates
+  e2e       frames/s through the reference-facing call surface Tracker.track(): H2D of the raw uint8 frames from pinned
+            memory, device crop/resize + engine + box update, D2H of the [B,10] result rows, prompt updates
   roofline  the GEMM kernel (dominant: ~75% of the step) timed live on this step's shapes vs the bf16 tensor peak;
             roofline_attention is the same for the fused attention kernel
   cpu_baseline  the numpy oracle of the same frame on the host cores, bounded sample
@@ -373,10 +373,13 @@ def run_b200(a):
                    "l2": "not flushed: every step streams the 273 MB bf16 weight set (> 126 MB L2) and rotates 4 input frames",
                    "vs_baseline_note": "value / 60 FPS = the reference's RTX-3090 profile_model.py figure for UVLTrack-B "
                                        "(z128/x256, forward_test only); this workload is the heavier 256/256 shape"},
-        "e2e": {"value": round(e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": B * dims.search_size ** 2 * 3,
-                "d2h_bytes_per_step": B * 24, "ms_per_step": round(e2e_s / a.steps * 1e3, 4),
-                "path": "BatchTracker.track(): OpenCV crop on host -> pinned uint8 -> uvlt_track_frame_host -> [B,6] rows "
-                        "-> host box update; prompt update every 20 frames; final trajectory all-gather included"},
+        "e2e": {"value": round(e2e, 2), "unit": "frames/s",
+                "h2d_bytes_per_step": int(B * np.prod(seqs[0][0][0].shape)),
+                "d2h_bytes_per_step": B * 80, "ms_per_step": round(e2e_s / a.steps * 1e3, 4),
+                "path": "BatchTracker.track(): raw uint8 frames (480x640x3) -> pinned staging -> H2D -> "
+                        "uvlt_track_frame_image_host (device crop+resize bit-exact with cv2, forward_test, window merge, "
+                        "map_box_back / clip_box) -> D2H of the [B,10] fp64 rows; prompt update every 20 frames; final "
+                        "trajectory all-gather included"},
         "gpu_launches": int(launches_per_step * a.steps + e2e_launches),
         "launches_per_step": int(launches_per_step),
         "clocks": clk, "roofline": roof, "roofline_attention": roof_a,

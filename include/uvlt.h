@@ -147,6 +147,29 @@ UVLT_API int uvlt_track_frame_host(uvlt_handle h, const uint8_t* search_u8_host,
                                    const double* window, int32_t batch, int32_t flags, int32_t has_cont,
                                    float* max_score, float* snapshot, float* out_host, void* stream);
 
+/* One tracker step with NOTHING but the frame upload on the host: raw uint8 RGB frames
+ * [B, frame_h, frame_w, 3] (HOST, pinned recommended; one size per call) are copied to the device, and there
+ *   sample_target (lib/train/data/processing_utils.py:159-243): crop of side ceil(sqrt(w*h)*search_factor) around the
+ *     box in `state`, zero padded, cv2.resize INTER_LINEAR fixed-point arithmetic reproduced bit for bit,
+ *   Preprocessor_wo_mask + forward_test + the window merge as in uvlt_track_frame_host,
+ *   pred_box * search_size / resize_factor, map_box_back, clip_box(margin 10) (lib/test/tracker/uvltrack.py:123-125,
+ *     :167-173, lib/utils/box_ops.py:117-126) in the reference's precisions (fp32 tensor ops, then fp64)
+ * run back to back.  `state` is DEVICE fp64 [B,4] (x, y, w, h in frame pixels), updated in place.
+ * out_host: HOST fp64 [B,10] = new state (4), network box cx cy w h (4), score, argmax index (-1 when the crop side
+ * is < 1 pixel: the reference raises "Too small bounding box.", the state is then left unchanged).
+ * Synchronises the stream before returning. */
+UVLT_API int uvlt_track_frame_image_host(uvlt_handle h, const uint8_t* frames_host, int32_t frame_h, int32_t frame_w,
+                                         double* state, double search_factor, const float* tmpl, const int64_t* ids,
+                                         const float* text_mask, const float* prompt, const int64_t* flag,
+                                         const double* window, int32_t batch, int32_t flags, int32_t has_cont,
+                                         float* max_score, float* snapshot, double* out_host, void* stream);
+
+/* sample_target alone (device pointers): frames uint8 [B,H,W,3], state fp64 [B,4] -> crops uint8 [B,S,S,3] and
+ * resize_factor fp64 [B] (0 when the crop side is < 1). */
+UVLT_API int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, const double* state,
+                                 double factor, int32_t out_size, uint8_t* crops, double* resize_factor, int32_t batch,
+                                 void* stream);
+
 /* number of kernels the last forward/track call launched (for bench.py's gpu_launches) */
 UVLT_API int uvlt_last_launch_count(uvlt_handle h);
 

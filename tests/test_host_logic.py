@@ -90,3 +90,43 @@ def test_synthetic_weights_are_deterministic_and_complete():
     assert pe.shape == (16, 768) and np.allclose(pe[0, :192], 0) and np.allclose(pe[0, 192:384], 1)  # sin(0), cos(0)
     inp = synthetic_inputs(d, 3, "MIXED", seed=1)
     assert inp["flag"].reshape(-1).tolist() == [0, 1, 2] and inp["text_mask"][0].sum() == 0 and inp["ids"][1, 0] == 101
+
+
+def test_opencv_linear_resize_fixed_point_model():
+    """The arithmetic csrc/track.cuh implements for cv2.resize(INTER_LINEAR) on 8-bit images (11-bit fixed-point taps,
+    x clamps index and weight, y clamps only the row index, VResizeLinear rounding) restated in numpy and pinned to the
+    OpenCV build in this image, for upscales, downscales and the identity."""
+    import cv2
+
+    F = np.float32
+
+    def taps(ssize, dsize, clamp):
+        scale = 1.0 / (dsize / ssize)
+        idx, a = np.zeros(dsize, np.int64), np.zeros((dsize, 2), np.int64)
+        for d in range(dsize):
+            f = F((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = F(f - F(s))
+            if clamp and s < 0:
+                f, s = F(0), 0
+            if clamp and s >= ssize - 1:
+                f, s = F(0), ssize - 1
+            idx[d] = s
+            a[d] = (int(np.rint(F(F(1.0) - f) * F(2048))), int(np.rint(f * F(2048))))
+        return idx, a
+
+    def resize(src, out):
+        h, w, _ = src.shape
+        xi, xa = taps(w, out, True)
+        yi, ya = taps(h, out, False)
+        s = src.astype(np.int64)
+        rows = s[:, xi, :] * xa[:, 0][None, :, None] + s[:, np.minimum(xi + 1, w - 1), :] * xa[:, 1][None, :, None]
+        s0, s1 = rows[np.clip(yi, 0, h - 1)], rows[np.clip(yi + 1, 0, h - 1)]
+        b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+        return ((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2).astype(np.uint8)
+
+    rng = np.random.default_rng(0)
+    for sz in (33, 100, 196, 255, 256, 257, 511, 777):
+        src = rng.integers(0, 256, (sz, sz, 3), dtype=np.uint8)
+        for out in (128, 256):
+            assert np.array_equal(resize(src, out), cv2.resize(src, (out, out))), (sz, out)

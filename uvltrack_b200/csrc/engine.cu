@@ -106,6 +106,10 @@ struct uvlt_engine {
   float* track_out = nullptr;
   int* snap_flag = nullptr;
   uint8_t* u8_stage = nullptr;
+  // device-resident tracker step (track.cuh)
+  uint8_t* frame_stage = nullptr;  // [B, H, W, 3] staging of the raw frames, grown on demand
+  size_t frame_stage_bytes = 0;
+  double *rf_d = nullptr, *out10_d = nullptr;
 
   cudaStream_t side = nullptr;
   cudaStream_t cap = nullptr;  // graphs are captured here (the caller's stream may be the legacy default stream)
@@ -161,6 +165,7 @@ int alloc_activations(uvlt_engine* e) {
   if (dalloc(e, &e->pr_src, B * 3 * D) || dalloc(e, &e->pr_src0, B * 3 * D) || dalloc(e, &e->pr_out, B * 3 * D) ||
       dalloc(e, &e->pr_src_bf, B * 3 * D) || dalloc(e, &e->pr_hid, B * 3 * Hd))
     return 1;
+  if (dalloc(e, &e->rf_d, B) || dalloc(e, &e->out10_d, B * 10)) return 1;
   if (dalloc(e, &e->track_out, B * 6) || dalloc(e, &e->snap_flag, B) ||
       dalloc(e, &e->u8_stage, B * static_cast<size_t>(e->Hx) * e->Hx * 3))
     return 1;
@@ -729,8 +734,14 @@ void fill_outputs(uvlt_engine* e, int B, uvlt_outputs* out, bool logits) {
 }
 
 int track_decode(uvlt_engine* e, cudaStream_t s, int B, const double* window, int has_cont, float* max_score,
-                 float* snapshot, float* out) {
+                 float* snapshot, float* out, double* state = nullptr, int frame_h = 0, int frame_w = 0) {
   DecodeParams dp{};
+  dp.state = state;
+  dp.rf = e->rf_d;
+  dp.frame_h = frame_h;
+  dp.frame_w = frame_w;
+  dp.search_size = e->Hx;
+  dp.out10 = e->out10_d;
   dp.cls_map = e->cls_map;
   dp.cont_prob = has_cont ? e->cont_prob : nullptr;
   dp.bbox_map = e->bbox_map;
@@ -805,6 +816,7 @@ void uvlt_destroy(uvlt_handle e) {
     for (auto& g : kv.second->graph)
       if (g) cudaGraphExecDestroy(g);
   for (void* p : e->allocs) cudaFree(p);
+  if (e->frame_stage) cudaFree(e->frame_stage);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->cap) cudaStreamDestroy(e->cap);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -978,6 +990,65 @@ int uvlt_track_frame_host(uvlt_handle e, const uint8_t* search_u8_host, const fl
   if (track_decode(e, s, B, window, has_cont, max_score, snapshot, e->track_out)) return 1;
   ENG_CUDA(cudaMemcpyAsync(out_host, e->track_out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
   ENG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32_t frame_h, int32_t frame_w,
+                                double* state, double search_factor, const float* tmpl, const int64_t* ids,
+                                const float* text_mask, const float* prompt, const int64_t* flag, const double* window,
+                                int32_t B, int32_t flags, int32_t has_cont, float* max_score, float* snapshot,
+                                double* out_host, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!frames_host || !state || !tmpl || !ids || !text_mask || !prompt || !flag || !window || !out_host) {
+    set_error("uvlt_track_frame_image_host: null argument");
+    return 1;
+  }
+  if (frame_h < 2 || frame_w < 2 || !(search_factor > 0.0)) {
+    set_error("uvlt_track_frame_image_host: bad frame size or search factor");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool skip_text = flags & UVLT_SKIP_TEXT;
+  Plan* p = get_plan(e, B, skip_text);
+  if (!p) return 1;
+  e->launch_count = 0;
+  const size_t bytes = static_cast<size_t>(B) * frame_h * frame_w * 3;
+  if (bytes > e->frame_stage_bytes) {  // first frame of a sequence (or a larger video): grow the staging buffer
+    ENG_CUDA(cudaStreamSynchronize(s));
+    if (e->frame_stage) cudaFree(e->frame_stage);
+    e->frame_stage = nullptr;
+    e->frame_stage_bytes = 0;
+    ENG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->frame_stage), bytes));
+    e->frame_stage_bytes = bytes;
+  }
+  ENG_CUDA(cudaMemcpyAsync(e->frame_stage, frames_host, bytes, cudaMemcpyHostToDevice, s));
+  CropParams cp{e->frame_stage, frame_h, frame_w, state, search_factor, e->Hx, e->u8_stage, e->rf_d};
+  UVLT_LAUNCH(crop_resize_kernel, dim3((e->Hx * e->Hx + 255) / 256, B), dim3(256), 0, s, cp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
+  ++e->launch_count;
+  if (stage_inputs(e, s, B, tmpl, nullptr, e->u8_stage, reinterpret_cast<const long long*>(ids), text_mask, prompt,
+                   reinterpret_cast<const long long*>(flag), skip_text))
+    return 1;
+  if (run_core(e, p, s, false, true)) return 1;
+  e->last_B = B;
+  e->last_cont_cols = e->cfg.softmax_one ? 3 : 2;
+  if (track_decode(e, s, B, window, has_cont, max_score, snapshot, e->track_out, state, frame_h, frame_w)) return 1;
+  ENG_CUDA(cudaMemcpyAsync(out_host, e->out10_d, static_cast<size_t>(B) * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  ENG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, const double* state, double factor,
+                        int32_t out_size, uint8_t* crops, double* resize_factor, int32_t B, void* stream) {
+  if (!frames || !state || !crops || !resize_factor || B < 1 || frame_h < 2 || frame_w < 2 || out_size < 1) {
+    set_error("uvlt_op_crop_resize: bad argument");
+    return 1;
+  }
+  CropParams cp{frames, frame_h, frame_w, state, factor, out_size, crops, resize_factor};
+  UVLT_LAUNCH(crop_resize_kernel, dim3((out_size * out_size + 255) / 256, B), dim3(256), 0,
+              static_cast<cudaStream_t>(stream), cp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
   return 0;
 }
 

@@ -3,6 +3,7 @@
 // All HBM-bound / latency-bound: one warp per search token, warp-shuffle reductions.
 #pragma once
 #include "common.cuh"
+#include "track.cuh"
 
 namespace uvlt {
 
@@ -142,6 +143,11 @@ struct DecodeParams {
   float* out;              // mode 0: [B, 4]; mode 1: [B, 6]
   float* max_score;        // mode 1, optional [B]: raised when the new score beats it (tracker :127-130)
   int* snap_flag;          // mode 1, optional [B]: 1 when the token stream of this sequence must be snapshotted
+  // mode 1, optional device-resident box state (track.cuh): when `state` is set the new box is computed here
+  double* state;           // [B, 4] x, y, w, h in frame pixels (in/out)
+  const double* rf;        // [B] resize factor of this frame's crop
+  int frame_h, frame_w, search_size;
+  double* out10;           // [B, 10] = new state (4), network box cx cy w h (4), score, argmax index
 };
 
 static __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p) {
@@ -187,6 +193,16 @@ static __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams p
         const bool better = p.max_score && score > p.max_score[b];
         p.snap_flag[b] = better ? 1 : 0;
         if (better) p.max_score[b] = score;
+      }
+      if (p.state) {
+        double* st = p.state + 4 * b;
+        double* o10 = p.out10 + 10 * b;
+        const double rf = p.rf[b];
+        if (rf > 0.0) box_update(bb, rf, p.search_size, p.frame_h, p.frame_w, st);
+        o10[0] = st[0]; o10[1] = st[1]; o10[2] = st[2]; o10[3] = st[3];
+        o10[4] = bb.x; o10[5] = bb.y; o10[6] = bb.z; o10[7] = bb.w;
+        o10[8] = score;
+        o10[9] = rf > 0.0 ? static_cast<double>(best_i) : -1.0;  // -1: "Too small bounding box." (crop side < 1)
       }
     }
   }

@@ -91,9 +91,12 @@ def extract_token_from_nlp(tokenizer, nlp: str, seq_length: int):
 class BatchTracker:
     """B independent sequences advanced in lock step on one GPU."""
 
-    def __init__(self, params, batch: int = 1, network=None):
+    def __init__(self, params, batch: int = 1, network=None, device_preprocess: bool = True):
         import torch
 
+        # device_preprocess: crop / resize / box update on the GPU (uvlt_track_frame_image_host); False keeps the
+        # reference's host pre/post-processing (OpenCV) around uvlt_track_frame_host.  Same boxes either way.
+        self.device_preprocess = bool(device_preprocess)
         self.params = params
         self.cfg = params.cfg
         self.B = int(batch)
@@ -136,6 +139,10 @@ class BatchTracker:
         self.crops_np = self.crops.numpy()
         self.out = torch.zeros(self.B, 6, dtype=torch.float32, pin_memory=True)
         self.out_np = self.out.numpy()
+        self.state_dev = torch.zeros(self.B, 4, dtype=torch.float64, device=dev)
+        self.out10 = torch.zeros(self.B, 10, dtype=torch.float64, pin_memory=True)
+        self.out10_np = self.out10.numpy()
+        self.frames = None  # pinned uint8 [B, H, W, 3], allocated for the first frame size seen
         self.skip_text = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -211,6 +218,7 @@ class BatchTracker:
         self.flag.copy_(torch.from_numpy(flags))
         self.template_mask.copy_(torch.from_numpy(tm_mask))
         self.max_score_dev.zero_()
+        self.state_dev.copy_(torch.tensor([[float(v) for v in st] for st in self.state], dtype=torch.float64))
         self.skip_text = bool((flags == 0).all())
         text = NestedTensor(self.ids, self.text_mask)
         self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx.cuda(), text, self.template_mask,
@@ -224,21 +232,49 @@ class BatchTracker:
 
         self.frame_id += 1
         S = self.params.search_size
-        rf = [0.0] * self.B
-        for b, image in enumerate(images):
-            crop, rf[b], _ = pp.sample_target(image, self.state[b], self.params.search_factor, S)
-            self.crops_np[b] = crop
-        self.engine.track_frame_host(self.crops, self.template, self.ids, self.text_mask, self.prompt, self.flag,
-                                     self.window_dev, self.out, self.B, has_cont=self.has_cont,
-                                     skip_text=self.skip_text, max_score=self.max_score_dev, snapshot=self.snapshot)
         results, update = [], []
-        for b, image in enumerate(images):
-            H, W = image.shape[:2]
-            row = self.out_np[b]
-            pred_box_net = row[:4].copy()
-            score = float(row[4])
-            pred_box = (pred_box_net * np.float32(S) / np.float32(rf[b])).tolist()
-            self.state[b] = pp.clip_box(pp.map_box_back(self.state[b], pred_box, rf[b], S), H, W, margin=10)
+        shapes = {im.shape for im in images}
+        if self.device_preprocess and len(shapes) == 1 and images[0].dtype == np.uint8 and images[0].ndim == 3:
+            # ---- everything but the frame upload on the device ----
+            H, W = images[0].shape[:2]
+            if self.frames is None or tuple(self.frames.shape[1:3]) != (H, W):
+                self.frames = torch.empty(self.B, H, W, 3, dtype=torch.uint8, pin_memory=True)
+                self.frames_np = self.frames.numpy()
+            for b, image in enumerate(images):
+                np.copyto(self.frames_np[b], image)
+            self.engine.track_frame_image_host(self.frames, self.state_dev, self.params.search_factor, self.template,
+                                               self.ids, self.text_mask, self.prompt, self.flag, self.window_dev,
+                                               self.out10, self.B, has_cont=self.has_cont, skip_text=self.skip_text,
+                                               max_score=self.max_score_dev, snapshot=self.snapshot)
+            rows = []
+            for b in range(self.B):
+                row = self.out10_np[b]
+                if row[9] < 0:
+                    raise Exception("Too small bounding box.")  # lib/train/data/processing_utils.py:180
+                self.state[b] = row[:4].tolist()
+                self.out_np[b, :4], self.out_np[b, 4], self.out_np[b, 5] = row[4:8], row[8], row[9]
+                rows.append((row[4:8].astype(np.float32), float(np.float32(row[8]))))
+        else:
+            # ---- the reference's host pre/post-processing around the device forward ----
+            rf = [0.0] * self.B
+            for b, image in enumerate(images):
+                crop, rf[b], _ = pp.sample_target(image, self.state[b], self.params.search_factor, S)
+                self.crops_np[b] = crop
+            self.engine.track_frame_host(self.crops, self.template, self.ids, self.text_mask, self.prompt, self.flag,
+                                         self.window_dev, self.out, self.B, has_cont=self.has_cont,
+                                         skip_text=self.skip_text, max_score=self.max_score_dev, snapshot=self.snapshot)
+            rows = []
+            for b, image in enumerate(images):
+                H, W = image.shape[:2]
+                row = self.out_np[b]
+                pred_box_net = row[:4].copy()
+                pred_box = (pred_box_net * np.float32(S) / np.float32(rf[b])).tolist()
+                self.state[b] = pp.clip_box(pp.map_box_back(self.state[b], pred_box, rf[b], S), H, W, margin=10)
+                rows.append((pred_box_net, float(row[4])))
+            if self.device_preprocess:
+                self.state_dev.copy_(torch.tensor(self.state, dtype=torch.float64))
+        for b in range(self.B):
+            pred_box_net, score = rows[b]
             if score > self.max_score[b] and self.has_cont:
                 self.pred_box_net[b] = pred_box_net
                 self.max_score[b] = score
@@ -266,7 +302,8 @@ class UVLTrack:
     def __init__(self, params, dataset_name=None, network=None):
         self.params = params
         self.cfg = params.cfg
-        self._bt = BatchTracker(params, batch=1, network=network)
+        self._bt = BatchTracker(params, batch=1, network=network,
+                                device_preprocess=getattr(params, "device_preprocess", True))
         self.network = self._bt.network
         self.debug = getattr(params, "debug", 0)
 
