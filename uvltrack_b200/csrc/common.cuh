@@ -19,6 +19,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// explicit shared-space 16-byte accesses (a pointer that went through integer arithmetic is generic to the compiler and
+// would be accessed with slow generic LD / ST)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -73,6 +84,27 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = g_pdl_enabled ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// ----------------------------------------------------------------------------------------------
+// Optional in-kernel timeline (debug builds only: make TRACE=1): CTA (0,0,0) of every traced kernel appends
+// (tag, SM clock, global ns timer) records; read back with uvlt_debug_trace().
+// ----------------------------------------------------------------------------------------------
+#ifdef UVLT_TRACE
+struct TraceRec { unsigned long long tag, clk, ns; };
+static __device__ TraceRec g_trace[4096];
+static __device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_pt(unsigned long long tag) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 4096) { g_trace[i].tag = tag; g_trace[i].clk = clock64(); g_trace[i].ns = ns; }
+  }
+}
+#define TRACE_PT(tag) trace_pt(tag)
+#else
+#define TRACE_PT(tag) ((void)0)
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier

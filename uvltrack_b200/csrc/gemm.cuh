@@ -50,18 +50,32 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;  // 2 * GEMM_MAX_STAGES + 1 mbarriers + the TMEM slot
-  // dynamic smem for a ring of `stages`: [<=1023 B align slack][ring, 1024-aligned][barriers]
-  static constexpr int total(int stages) { return stages * STAGE_BYTES + 1024 + BAR_BYTES; }
-  // throughput configuration: ~96 KB of ring -> two CTAs per SM, one CTA's epilogue overlaps the other's mainloop
-  static constexpr int STAGES_2CTA = (96 * 1024) / STAGE_BYTES > 8 ? 8 : (96 * 1024) / STAGE_BYTES;
-  // latency configuration (grid <= one CTA per SM): as much of K in flight as fits in 227 KB
-  static constexpr int STAGES_1CTA =
-      (224 * 1024 - 1024 - BAR_BYTES) / STAGE_BYTES > GEMM_MAX_STAGES ? GEMM_MAX_STAGES
-                                                                     : (224 * 1024 - 1024 - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;   // 2 * GEMM_MAX_STAGES + 1 mbarriers + the TMEM slot
+  static constexpr int BIAS_BYTES = BN * 4;
+  static constexpr int EPI_BYTES = GEMM_BM * BN * 4;  // fp32 staging tile of the epilogue, aliases the operand ring
+  // dynamic smem for a ring of `stages`: [ring, 1024-aligned][barriers][bias]
+  static constexpr int total(int stages) {
+    return (stages * STAGE_BYTES > EPI_BYTES ? stages * STAGE_BYTES : EPI_BYTES) + BAR_BYTES + BIAS_BYTES;
+  }
+  // ~100 KB of ring -> two CTAs per SM: one CTA's epilogue overlaps the other's mainloop, and under programmatic
+  // dependent launch the next kernel's CTAs become resident (and prefetch their weight tiles) while this one runs
+  static constexpr int STAGES_2CTA = (108 * 1024) / STAGE_BYTES > 8 ? 8 : (108 * 1024) / STAGE_BYTES;
+  static_assert(STAGES_2CTA * STAGE_BYTES >= EPI_BYTES, "epilogue staging must fit in the ring");
 };
 
-template <int BN>
+// Epilogue flavours (compile-time, so that each instantiation carries only its own code: these kernels run every code
+// path once per CTA, i.e. with a cold instruction cache at batch 1 -- code size is latency here).
+enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_RELU = 2, EPI_F32 = 3 };
+//   EPI_BF16*  : out bf16 [M, out_ld] (+ group column offset), bias, optional activation
+//   EPI_F32    : out fp32 with the optional row remap into the [B, N, D] residual stream, bias, optional fp32 residual
+//                (same-row in-place residual, or a periodic table such as the positional embedding)
+
+static __device__ __noinline__ float4 gelu4(float4 v) {
+  v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+  return v;
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                     const GemmShape shape, const GemmEpilogue ep) {
@@ -69,13 +83,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int STAGES = shape.stages;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
-  extern __shared__ uint8_t smem_raw[];
-  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t gemm_smem[];  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
+  uint8_t* const smem = gemm_smem;
+  const int ring_bytes = STAGES * S::STAGE_BYTES > S::EPI_BYTES ? STAGES * S::STAGE_BYTES : S::EPI_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* acc_bar = empty_bar + GEMM_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + ring_bytes + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,40 +98,57 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int m0 = blockIdx.y * GEMM_BM;
   const int g = blockIdx.z;
   const int num_kb = shape.K / GEMM_BK;
+  const int pre = num_kb < STAGES ? num_kb : STAGES;  // k-blocks whose weight tile is requested before pdl_wait
+  if (threadIdx.x == 0) TRACE_PT(0x100);
 
+  // ---- prologue: touches only weights (W tiles, bias), so under PDL it overlaps the predecessor kernel ----
   if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();  // dynamic shared memory must be 1024-byte aligned
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
+#pragma unroll 1
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
+#pragma unroll 1
+    for (int kb = 0; kb < pre; ++kb) {
+      mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);  // A + W bytes; the A half is issued after pdl_wait
+      tma_load_3d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tma_w, &full_bar[kb], kb * GEMM_BK, n0, g);
+    }
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN)
+    s_bias[threadIdx.x - 64] = ep.bias ? __ldg(ep.bias + g * ep.bias_gstride + n0 + (threadIdx.x - 64)) : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
-  pdl_wait();     // everything above overlapped the predecessor's tail; A / residual are only read below
+  if (threadIdx.x == 0) TRACE_PT(0x101);
+  pdl_wait();     // A and the residual come from earlier kernels of the chain: nothing below may move above this
   pdl_trigger();
+  if (threadIdx.x == 0) TRACE_PT(0x102);
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      int s = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], kb * GEMM_BK, m0, g);
+      int s = 0;              // pre == STAGES whenever the loop below runs
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+#pragma unroll 1
+      for (int kb = pre; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + S::A_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         tma_load_3d(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
-        tma_load_3d(b_dst, &tma_w, &full_bar[s], kb * GEMM_BK, n0, g);
+        tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0, g);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -126,9 +158,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0);
       int s = 0;
       uint32_t ph = 0;
+#pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (kb == 0) TRACE_PT(0x103);
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
         const uint64_t adesc = umma_smem_desc_sw128(a_addr, 1024, 0);
@@ -142,77 +176,138 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(acc_bar);  // accumulator complete
+      TRACE_PT(0x104);
     }
   } else {
     // ---------------- epilogue warps ----------------
+    // Stage 1 (thread = accumulator row): TMEM -> registers, + bias -> fp32 staging tile in the (now idle) operand
+    // ring, 16-byte chunks XOR-swizzled with the row so that both stages are bank-conflict free.
+    // Stage 2 (lanes across columns): activation, coalesced residual read / add, convert, store -- whole rows per warp
+    // instruction (a row-per-thread store costs 32 L1 wavefronts per instruction instead of 2-4).
     const int lane_grp = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row_in_tile = lane_grp * 32 + lane;
-    const int r = m0 + row_in_tile;
+    constexpr bool F32 = (EPI == EPI_F32);
+    constexpr int ESZ = F32 ? 4 : 2;            // staged element size: the bf16 flavours convert in stage 1
+    constexpr int ROWB = BN * ESZ;              // bytes per staged row
+    constexpr int CPR = ROWB / 16;              // 16-byte chunks per staged row
+    constexpr int RPI = 32 / CPR;               // rows covered by one warp instruction in stage 2
+    constexpr int ITERS = 32 / RPI;
+    constexpr int SWZ = (CPR < 8 ? CPR : 8) - 1;  // XOR swizzle of the chunk index with the row, kept inside the row
+    const uint32_t stage_w = smem_u32(smem) + lane_grp * 32 * ROWB;  // this warp's 32 rows of the staging tile
+    const int j2 = lane % CPR;
+    const int col = n0 + j2 * (16 / ESZ);
+    const int r_first = m0 + lane_grp * 32 + lane / CPR;  // this lane's rows are r_first + it * RPI
+    // position of the first row inside its sequence / inside the periodic residual table, computed while the mainloop
+    // runs; advanced incrementally afterwards (the periods are >= 8 rows on this path, checked on the host)
+    int seq_q = 0, seq_rem = r_first, per_rem = 0;
+    if (F32) {
+      if (ep.in_rows_per_b > 0) { seq_q = r_first / ep.in_rows_per_b; seq_rem = r_first - seq_q * ep.in_rows_per_b; }
+      if (ep.resid_period > 0) per_rem = r_first % ep.resid_period;
+    }
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const bool row_ok = r < shape.M;
-    long long out_row = r;
-    if (ep.in_rows_per_b > 0) {
-      out_row = static_cast<long long>(r / ep.in_rows_per_b) * ep.out_rows_per_b + ep.out_row_off +
-                (r % ep.in_rows_per_b);
-    }
-    const float* bias = ep.bias ? ep.bias + g * ep.bias_gstride + n0 : nullptr;
-    const float* resid = nullptr;
-    if (ep.resid) {
-      const long long rr = ep.resid_period > 0 ? (r % ep.resid_period) : out_row;
-      resid = ep.resid + rr * ep.resid_ld + n0;
-    }
-    constexpr int CH = BN < 32 ? BN : 32;
+    if (threadIdx.x == 64) TRACE_PT(0x105);
+    {
+      const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16);
+      const uint32_t my_row = stage_w + lane * ROWB;
+      uint32_t va[32], vb[32];
+      // 32 accumulator columns: + bias (+ activation, -> bf16) -> swizzled staging row
+      auto stage1 = [&](uint32_t (&v)[32], int c) {
+        if (F32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+            const int j = ((c >> 2) + q) ^ (lane & SWZ);
+            sts128(my_row + j * 16, __uint_as_float(v[q * 4]) + b4.x, __uint_as_float(v[q * 4 + 1]) + b4.y,
+                   __uint_as_float(v[q * 4 + 2]) + b4.z, __uint_as_float(v[q * 4 + 3]) + b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 x0 = *reinterpret_cast<const float4*>(s_bias + c + q * 8);
+            float4 x1 = *reinterpret_cast<const float4*>(s_bias + c + q * 8 + 4);
+            x0.x += __uint_as_float(v[q * 8]);     x0.y += __uint_as_float(v[q * 8 + 1]);
+            x0.z += __uint_as_float(v[q * 8 + 2]); x0.w += __uint_as_float(v[q * 8 + 3]);
+            x1.x += __uint_as_float(v[q * 8 + 4]); x1.y += __uint_as_float(v[q * 8 + 5]);
+            x1.z += __uint_as_float(v[q * 8 + 6]); x1.w += __uint_as_float(v[q * 8 + 7]);
+            if (EPI == EPI_BF16_GELU) { x0 = gelu4(x0); x1 = gelu4(x1); }
+            if (EPI == EPI_BF16_RELU) {
+              x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+              x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+            }
+            const int j = ((c >> 3) + q) ^ (lane & SWZ);
+            sts128(my_row + j * 16, __uint_as_float(pack_bf16x2(x0.x, x0.y)), __uint_as_float(pack_bf16x2(x0.z, x0.w)),
+                   __uint_as_float(pack_bf16x2(x1.x, x1.y)), __uint_as_float(pack_bf16x2(x1.z, x1.w)));
+          }
+        }
+      };
+      tmem_ld32(t_row, va);
+      tmem_wait_ld_dep(va);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + c, v);
-      tmem_wait_ld();
-      if (!row_ok) continue;
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) f[i] = __uint_as_float(v[i]);
-      if (bias) {
-#pragma unroll
-        for (int i = 0; i < CH; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c + i));
-          f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-        }
-      }
-      if (ep.act == ACT_GELU) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) f[i] = gelu_erf(f[i]);
-      } else if (ep.act == ACT_RELU) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) f[i] = fmaxf(f[i], 0.0f);
-      }
-      if (resid) {
-#pragma unroll
-        for (int i = 0; i < CH; i += 4) {
-          const float4 r4 = *reinterpret_cast<const float4*>(resid + c + i);
-          f[i] += r4.x; f[i + 1] += r4.y; f[i + 2] += r4.z; f[i + 3] += r4.w;
-        }
-      }
-      if (ep.out_f32) {
-        float* o = reinterpret_cast<float*>(ep.out) + g * ep.out_gstride + out_row * ep.out_ld + n0 + c;
-#pragma unroll
-        for (int i = 0; i < CH; i += 4)
-          *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-      } else {
-        __nv_bfloat16* o =
-            reinterpret_cast<__nv_bfloat16*>(ep.out) + g * ep.out_gstride + out_row * ep.out_ld + n0 + c;
-#pragma unroll
-        for (int i = 0; i < CH; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(f[i], f[i + 1]);
-          u.y = pack_bf16x2(f[i + 2], f[i + 3]);
-          u.z = pack_bf16x2(f[i + 4], f[i + 5]);
-          u.w = pack_bf16x2(f[i + 6], f[i + 7]);
-          *reinterpret_cast<uint4*>(o + i) = u;
+      for (int c = 0; c < BN; c += 64) {
+        if (c + 32 < BN) tmem_ld32(t_row + c + 32, vb);
+        stage1(va, c);
+        if (c + 32 < BN) {
+          tmem_wait_ld_dep(vb);
+          if (c + 64 < BN) tmem_ld32(t_row + c + 64, va);
+          stage1(vb, c + 32);
+          if (c + 64 < BN) tmem_wait_ld_dep(va);
         }
       }
     }
     tc_fence_before();
+    __syncwarp();
+    if (threadIdx.x == 64) TRACE_PT(0x108);
+    {
+      const int rows_left = shape.M - r_first;
+      const uint32_t src = stage_w + (lane / CPR) * ROWB;
+      constexpr int UN = ITERS < 4 ? ITERS : 4;
+#pragma unroll 1
+      for (int it0 = 0; it0 < ITERS; it0 += UN) {
+        float4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int row_l = (it0 + u) * RPI + lane / CPR;
+          v[u] = lds128(src + (it0 + u) * RPI * ROWB + ((j2 ^ (row_l & SWZ)) * 16));
+        }
+        if (F32) {
+          long long orow[UN];
+          float4 r4[UN];
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const bool ok = (it0 + u) * RPI < rows_left;
+            if (ep.in_rows_per_b > 0) {
+              if (seq_rem >= ep.in_rows_per_b) { seq_rem -= ep.in_rows_per_b; ++seq_q; }
+              orow[u] = static_cast<long long>(seq_q) * ep.out_rows_per_b + ep.out_row_off + seq_rem;
+            } else {
+              orow[u] = seq_rem;
+            }
+            seq_rem += RPI;
+            long long rr = orow[u];
+            if (ep.resid_period > 0) {
+              if (per_rem >= ep.resid_period) per_rem -= ep.resid_period;
+              rr = per_rem;
+              per_rem += RPI;
+            }
+            r4[u] = (ep.resid && ok) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            if ((it0 + u) * RPI >= rows_left) continue;
+            v[u].x += r4[u].x; v[u].y += r4[u].y; v[u].z += r4[u].z; v[u].w += r4[u].w;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + g * ep.out_gstride + orow[u] * ep.out_ld + col) = v[u];
+          }
+        } else {
+          __nv_bfloat16* const o = reinterpret_cast<__nv_bfloat16*>(ep.out) + g * ep.out_gstride + col;
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            if ((it0 + u) * RPI >= rows_left) continue;
+            *reinterpret_cast<float4*>(o + static_cast<long long>(r_first + (it0 + u) * RPI) * ep.out_ld) = v[u];
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 64) TRACE_PT(0x106);
   }
 
   __syncthreads();
@@ -220,6 +315,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_acc, TMEM_COLS);
   }
+  if (threadIdx.x == 64) TRACE_PT(0x107);
 }
 
 }  // namespace uvlt

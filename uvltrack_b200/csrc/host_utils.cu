@@ -56,12 +56,14 @@ int init_kernel_attributes() {
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   if (status == 0) return 0;
-  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<32>::total(GemmSmem<32>::STAGES_1CTA)));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<64>::total(GemmSmem<64>::STAGES_1CTA)));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmSmem<128>::total(GemmSmem<128>::STAGES_1CTA)));
+#define UVLT_GEMM_ATTR(BN, EPI)                                                                              \
+  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    GemmSmem<BN>::total(GemmSmem<BN>::STAGES_2CTA)))
+#define UVLT_GEMM_ATTR_BN(BN) \
+  UVLT_GEMM_ATTR(BN, EPI_BF16); UVLT_GEMM_ATTR(BN, EPI_BF16_GELU); UVLT_GEMM_ATTR(BN, EPI_BF16_RELU); UVLT_GEMM_ATTR(BN, EPI_F32)
+  UVLT_GEMM_ATTR_BN(32);
+  UVLT_GEMM_ATTR_BN(64);
+  UVLT_GEMM_ATTR_BN(128);
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
@@ -70,7 +72,7 @@ int init_kernel_attributes() {
 }
 
 int pick_bn(int M, int N, int groups) {
-  // Widest tile that still gives >= 90 CTAs (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
+  // Widest tile that still gives one CTA per SM (148) (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
   // which bounds these launches, until fewer than ~2/3 of the SMs have work); below that, the narrowest legal tile.
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int cands[3] = {128, 64, 32};
@@ -78,7 +80,7 @@ int pick_bn(int M, int N, int groups) {
   for (int bn : cands) {
     if (N % bn) continue;
     best = bn;
-    if (static_cast<long long>(m_tiles) * (N / bn) * groups >= 90) break;
+    if (static_cast<long long>(m_tiles) * (N / bn) * groups >= 148) break;
   }
   return best;
 }
@@ -95,16 +97,25 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
               " K=" + std::to_string(K) + ")");
     return 1;
   }
+  // epilogue flavours the kernel is instantiated for (gemm.cuh): bf16 out = bias + activation only;
+  // fp32 out = bias + optional residual + optional row remap, no activation
+  if (!ep.out_f32 && (ep.resid || ep.in_rows_per_b > 0)) {
+    set_error("gemm: a residual / row remap needs an fp32 output");
+    return 1;
+  }
+  if (ep.out_f32 && ep.act != ACT_NONE) {
+    set_error("gemm: activations are only fused with a bf16 output");
+    return 1;
+  }
+  if ((ep.in_rows_per_b > 0 && ep.in_rows_per_b < 8) || (ep.resid_period > 0 && ep.resid_period < 8)) {
+    set_error("gemm: row remap / residual periods must be >= 8 rows");
+    return 1;
+  }
   g->shape = GemmShape{M, N, K, 0};
   {
-    // ring depth: a grid that fits one CTA per SM is latency bound -> put as much of K in flight as shared memory
-    // allows; larger grids keep ~96 KB rings so two CTAs share an SM and overlap epilogue with mainloop
-    const long long tiles = static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / bn) * groups;
-    const int s1 = bn == 32 ? GemmSmem<32>::STAGES_1CTA : bn == 64 ? GemmSmem<64>::STAGES_1CTA : GemmSmem<128>::STAGES_1CTA;
+    // ring depth: ~100 KB so that two CTAs share an SM (epilogue / mainloop overlap, and PDL residency of the next kernel)
     const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA : GemmSmem<128>::STAGES_2CTA;
-    int st = tiles <= 148 ? s1 : s2;
-    st = std::min(st, K / GEMM_BK);
-    g->shape.stages = std::max(st, 1);
+    g->shape.stages = std::max(std::min(s2, K / GEMM_BK), 1);
   }
   g->ep = ep;
   g->bn = bn;
@@ -115,18 +126,27 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   return 0;
 }
 
+template <int BN>
+static void gemm_launch_bn(const GemmLaunch& g, dim3 grid, cudaStream_t stream) {
+  const size_t smem = GemmSmem<BN>::total(g.shape.stages);
+  const dim3 block(GEMM_THREADS);
+  if (g.ep.out_f32) {
+    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_F32>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+  } else if (g.ep.act == ACT_GELU) {
+    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16_GELU>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+  } else if (g.ep.act == ACT_RELU) {
+    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16_RELU>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+  } else {
+    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+  }
+}
+
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups);
   switch (g.bn) {
-    case 32:
-      UVLT_LAUNCH(gemm_bf16_tn_kernel<32>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<32>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
-      break;
-    case 64:
-      UVLT_LAUNCH(gemm_bf16_tn_kernel<64>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<64>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
-      break;
-    default:
-      UVLT_LAUNCH(gemm_bf16_tn_kernel<128>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<128>::total(g.shape.stages), stream, g.tma_a, g.tma_w, g.shape, g.ep);
-      break;
+    case 32: gemm_launch_bn<32>(g, grid, stream); break;
+    case 64: gemm_launch_bn<64>(g, grid, stream); break;
+    default: gemm_launch_bn<128>(g, grid, stream); break;
   }
   UVLT_CUDA_OK(cudaGetLastError());
   return 0;
@@ -163,3 +183,18 @@ int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
 }
 
 }  // namespace uvlt
+
+#ifdef UVLT_TRACE
+// debug builds only (make TRACE=1): copy out and reset the in-kernel timeline; out = [n][3] uint64 (tag, clk, ns)
+extern "C" __attribute__((visibility("default"))) int uvlt_debug_trace(unsigned long long* out, int max_recs) {
+  cudaDeviceSynchronize();
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, uvlt::g_trace_n, sizeof(n));
+  if (n > 4096u) n = 4096u;
+  if (static_cast<int>(n) > max_recs) n = max_recs;
+  cudaMemcpyFromSymbol(out, uvlt::g_trace, sizeof(uvlt::TraceRec) * n);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(uvlt::g_trace_n, &zero, sizeof(zero));
+  return static_cast<int>(n);
+}
+#endif

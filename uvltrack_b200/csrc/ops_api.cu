@@ -13,6 +13,8 @@ const char* uvlt_last_error(void) { return get_error(); }
 
 int uvlt_abi_version(void) { return UVLT_ABI_VERSION; }
 
+
+
 int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* resid, void* out, int M, int N, int K,
                  int act, int out_f32, int bn, void* stream) {
   if (init_kernel_attributes()) return 1;
