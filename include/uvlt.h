@@ -78,7 +78,8 @@ UVLT_API int uvlt_set_weight(uvlt_handle h, const char* key, const float* data, 
 UVLT_API int uvlt_finalize_weights(uvlt_handle h);
 
 /* options: "graph" (1: replay the layer chain as a CUDA graph, default 1), "bn" (force GEMM tile width, 0 = auto),
- * "pdl" (1: programmatic dependent launch between the kernels of the chain, default 1; process-wide) */
+ * "pdl" (1: programmatic dependent launch between the kernels of the chain, default 1; process-wide),
+ * "splitk" (1: split-K fc2 at small batch with the partials summed by the next LayerNorm, default 1) */
 UVLT_API int uvlt_set_option(uvlt_handle h, const char* name, int32_t value);
 
 typedef struct uvlt_outputs {

@@ -32,9 +32,9 @@ def test_forward_test_vs_oracle(z, x, B, mode, variant):
     if variant == "no_softmax_one":
         dims.softmax_one = False
         cfg.MODEL.HEAD.SOFTMAX_ONE = False
-    # cls_sharpen=2 (default 4): the sharpening gain of the synthetic cls tower multiplies the bf16 feature error into
+    # cls_sharpen=1 (default 4): the sharpening gain of the synthetic cls tower multiplies the bf16 feature error into
     # the score map; the peaked map it buys is only needed by the argmax / box tests, not by this tensor comparison
-    sd = synthetic_state_dict(dims, seed=11, cls_sharpen=2.0)
+    sd = synthetic_state_dict(dims, seed=11, cls_sharpen=1.0)
     inp = synthetic_inputs(dims, B, mode, seed=11)
     model = registry.MODELS["uvltrack"](cfg, max_batch=B)
     model.load_state_dict(sd)

@@ -58,6 +58,9 @@ struct Plan {
   GemmLaunch pr_fc1, pr_fc2;
   std::vector<AttnLaunch> vit_attn;  // depth
   AttnLaunch bert_attn;
+  std::vector<int> vit_fc2_splits;   // split-K factor of each layer's fc2 (its partials are summed by the next LayerNorm)
+  int bert_fc2_splits = 1;
+  bool exact_stream = false;         // partials are summed right after fc2 (the per-layer logits read the stream)
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [want_logits]
   int graph_kernels[2] = {0, 0};
 };
@@ -71,6 +74,7 @@ struct uvlt_engine {
   bool finalized = false;
   bool use_graph = true;
   int force_bn = 0;
+  bool no_splitk = false;
   int launch_count = 0;
 
   std::unordered_map<std::string, HostTensor> staged;
@@ -93,6 +97,7 @@ struct uvlt_engine {
 
   // activations
   float* x = nullptr;
+  float* xpart = nullptr;  // [3][B, N, D] split-K partial products of fc2 (same offsets as x)
   __nv_bfloat16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *pcol = nullptr;
   __nv_bfloat16 *t_a = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_hid = nullptr;
   float *bias_vis = nullptr, *bias_joint = nullptr, *bias_bert = nullptr;
@@ -143,6 +148,7 @@ int alloc_activations(uvlt_engine* e) {
   const size_t B = e->Bm, N = e->N, D = e->D, Hd = e->Hd, T = e->T, SS = e->SS, C = e->C;
   if (dalloc(e, &e->x, B * N * D)) return 1;
   ENG_CUDA(cudaMemset(e->x, 0, B * N * D * sizeof(float)));
+  if (dalloc(e, &e->xpart, 3 * B * N * D)) return 1;
   if (dalloc(e, &e->a, B * N * D) || dalloc(e, &e->qkv, B * N * 3 * D) || dalloc(e, &e->att, B * N * D) ||
       dalloc(e, &e->hid, B * N * Hd) || dalloc(e, &e->pcol, B * (e->Nz + e->Nx) * 768))
     return 1;
@@ -376,17 +382,22 @@ GemmEpilogue ep_stream(uvlt_engine* e, const float* bias, int rows, int row_off)
   ep.in_rows_per_b = rows;
   ep.out_rows_per_b = e->N;
   ep.out_row_off = row_off;
+  ep.split_out = e->xpart;
+  ep.split_stride = static_cast<long long>(e->Bm) * e->N * e->D;
   return ep;
 }
 
-Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
-  const int key = B * 2 + (skip_text ? 1 : 0);
+// `exact_stream`: the token stream must be complete after every layer (per-layer contrastive logits read it), so fc2 is
+// not split
+Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false) {
+  const int key = B * 4 + (skip_text ? 2 : 0) + (exact_stream ? 1 : 0);
   auto it = e->plans.find(key);
   if (it != e->plans.end()) return it->second.get();
   auto plan = std::make_unique<Plan>();
   Plan* p = plan.get();
   p->B = B;
   p->skip_text = skip_text;
+  p->exact_stream = exact_stream;
   const int D = e->D, Hd = e->Hd, Nv = e->Nv, N = e->N, T = e->T;
   {
     GemmEpilogue ep{};
@@ -404,6 +415,7 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
   }
   p->vit.resize(e->L);
   p->vit_attn.resize(e->L);
+  p->vit_fc2_splits.assign(e->L, 1);
   for (int i = 0; i < e->L; ++i) {
     const bool joint = (i >= e->F0) && !skip_text;
     const int rows = joint ? N : Nv;
@@ -413,7 +425,14 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
     if (prep(e, &lp.qkv, e->a, w.qkv_w, M, 3 * D, D, ep_bf16(w.qkv_b, e->qkv, 3 * D, ACT_NONE))) return nullptr;
     if (prep(e, &lp.proj, e->att, w.proj_w, M, D, D, ep_stream(e, w.proj_b, rows, 0))) return nullptr;
     if (prep(e, &lp.fc1, e->a, w.fc1_w, M, Hd, D, ep_bf16(w.fc1_b, e->hid, Hd, ACT_GELU))) return nullptr;
-    if (prep(e, &lp.fc2, e->hid, w.fc2_w, M, D, Hd, ep_stream(e, w.fc2_b, rows, 0))) return nullptr;
+    // the last layer's stream is read by the head / returned to the caller: complete it inside the GEMM
+    // The split factor is chosen for the engine's max_batch, not for this call's batch, so that a sequence's result
+    // does not depend on how many sequences share the call (the reduction order is part of the result).
+    const int sk = (e->no_splitk || i == e->L - 1) ? 1 : pick_splits(e->Bm * rows, D, Hd);
+    p->vit_fc2_splits[i] = sk;
+    if (gemm_prepare(&lp.fc2, e->hid, Hd, 0, w.fc2_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 128 : e->force_bn,
+                     ep_stream(e, w.fc2_b, rows, 0), sk))
+      return nullptr;
     if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0))
       return nullptr;
   }
@@ -426,7 +445,11 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
       if (prep(e, &lp.qkv, e->t_a, w.qkv_w, M, 3 * D, D, ep_bf16(w.qkv_b, e->t_qkv, 3 * D, ACT_NONE))) return nullptr;
       if (prep(e, &lp.proj, e->t_att, w.ao_w, M, D, D, ep_stream(e, w.ao_b, T, Nv))) return nullptr;
       if (prep(e, &lp.fc1, e->t_a, w.in_w, M, Hd, D, ep_bf16(w.in_b, e->t_hid, Hd, ACT_GELU))) return nullptr;
-      if (prep(e, &lp.fc2, e->t_hid, w.out_w, M, D, Hd, ep_stream(e, w.out_b, T, Nv))) return nullptr;
+      const int sk = e->no_splitk ? 1 : pick_splits(e->Bm * T, D, Hd);
+      p->bert_fc2_splits = sk;
+      if (gemm_prepare(&lp.fc2, e->t_hid, Hd, 0, w.out_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 128 : e->force_bn,
+                       ep_stream(e, w.out_b, T, Nv), sk))
+        return nullptr;
     }
     if (attn_prepare(&p->bert_attn, e->t_qkv, B, T, e->H, e->bias_bert, e->t_att, nullptr, 0)) return nullptr;
   }
@@ -474,8 +497,13 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text) {
   } while (0)
 
 int ln(uvlt_engine* e, cudaStream_t s, int B, int row_off, int rows, const float* g, const float* b, float eps,
-       int mode, __nv_bfloat16* dst, const float* add0, const float* add1, int split) {
+       int mode, __nv_bfloat16* dst, const float* add0, const float* add1, int split, int n_partials = 0,
+       int partial_rows = 0) {
   LnParams p{};
+  p.partials = e->xpart;
+  p.n_partials = n_partials;
+  p.partial_rows = partial_rows;
+  p.partial_stride = static_cast<long long>(e->Bm) * e->N * e->D;
   p.x = e->x;
   p.x_bstride = static_cast<long long>(e->N) * e->D;
   p.x_row_off = row_off;
@@ -527,7 +555,7 @@ int bert_layer(uvlt_engine* e, Plan* p, cudaStream_t t, int i) {
   RUN(ln(e, t, B, Nv, T, w.ao_g, w.ao_beta, 1e-12f, 2, e->t_a, nullptr, nullptr, 0));
   RUN(gemm_launch(lp.fc1, t));
   RUN(gemm_launch(lp.fc2, t));
-  RUN(ln(e, t, B, Nv, T, w.out_g, w.out_beta, 1e-12f, 2, e->t_a, nullptr, nullptr, 0));
+  RUN(ln(e, t, B, Nv, T, w.out_g, w.out_beta, 1e-12f, 2, e->t_a, nullptr, nullptr, 0, p->bert_fc2_splits - 1, T));
   return 0;
 }
 
@@ -538,14 +566,20 @@ int vit_layer(uvlt_engine* e, Plan* p, cudaStream_t s, int i) {
   const bool fusion = i >= e->F0;
   const int rows = (fusion && !p->skip_text) ? N : Nv;
   // fusion layers add the modality embeddings to the stream first and keep them (mae_vit.py:196)
+  // rows whose last fc2 (previous layer) left split-K partials behind: summed here.  In the first fusion layer only the
+  // image rows have pending partials (the text rows were completed by the BERT branch's own LayerNorm).
+  const int prev_sk = (i > 0 && !p->exact_stream) ? p->vit_fc2_splits[i - 1] : 1;
+  const int prev_rows = (i > e->F0 && !p->skip_text) ? N : Nv;
   RUN(ln(e, s, B, 0, rows, w.ln1_g, w.ln1_b, 1e-6f, fusion ? 1 : 0, e->a, fusion ? e->modal : nullptr,
-         fusion ? e->modal + e->D : nullptr, Nv));
+         fusion ? e->modal + e->D : nullptr, Nv, prev_sk - 1, prev_rows));
   RUN(gemm_launch(lp.qkv, s));
   RUN(attn_launch(p->vit_attn[i], s));
   RUN(gemm_launch(lp.proj, s));
   RUN(ln(e, s, B, 0, rows, w.ln2_g, w.ln2_b, 1e-6f, 0, e->a, nullptr, nullptr, 0));
   RUN(gemm_launch(lp.fc1, s));
   RUN(gemm_launch(lp.fc2, s));
+  if (p->exact_stream && p->vit_fc2_splits[i] > 1)  // complete the stream now (same summation order as the next LN1)
+    RUN(ln(e, s, B, 0, rows, w.ln2_g, w.ln2_b, 1e-6f, 0, nullptr, nullptr, nullptr, 0, p->vit_fc2_splits[i] - 1, rows));
   return 0;
 }
 
@@ -856,7 +890,14 @@ int uvlt_set_option(uvlt_handle e, const char* name, int32_t value) {
   if (!e || !name) { set_error("uvlt_set_option: null argument"); return 1; }
   const std::string n(name);
   if (n == "graph") e->use_graph = value != 0;
-  else if (n == "pdl") {
+  else if (n == "splitk") {
+    e->no_splitk = value == 0;
+    cudaDeviceSynchronize();
+    for (auto& kv : e->plans)
+      for (auto& g : kv.second->graph)
+        if (g) cudaGraphExecDestroy(g);
+    e->plans.clear();
+  } else if (n == "pdl") {
     // programmatic dependent launch for every kernel of the chain (process-wide); captured graphs must be rebuilt
     g_pdl_enabled = value != 0;
     cudaDeviceSynchronize();
@@ -883,7 +924,7 @@ int uvlt_forward_test(uvlt_handle e, const float* tmpl, const float* search, con
   if (!tmpl || !search || !ids || !text_mask || !prompt || !flag) { set_error("uvlt_forward_test: null input"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool skip_text = flags & UVLT_SKIP_TEXT, logits = flags & UVLT_WANT_LOGITS;
-  Plan* p = get_plan(e, B, skip_text);
+  Plan* p = get_plan(e, B, skip_text, logits);
   if (!p) return 1;
   e->launch_count = 0;
   if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, prompt,
@@ -903,7 +944,7 @@ int uvlt_backbone(uvlt_handle e, const float* tmpl, const float* search, const i
   if (!tmpl || !search || !ids || !text_mask || !flag) { set_error("uvlt_backbone: null input"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool skip_text = flags & UVLT_SKIP_TEXT, logits = flags & UVLT_WANT_LOGITS;
-  Plan* p = get_plan(e, B, skip_text);
+  Plan* p = get_plan(e, B, skip_text, logits);
   if (!p) return 1;
   e->launch_count = 0;
   if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, nullptr,
@@ -926,7 +967,7 @@ int uvlt_forward_train(uvlt_handle e, const float* tmpl, const float* search, co
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool logits = flags & UVLT_WANT_LOGITS;
-  Plan* p = get_plan(e, B, false);
+  Plan* p = get_plan(e, B, false, logits);
   if (!p) return 1;
   e->launch_count = 0;
   if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, nullptr,

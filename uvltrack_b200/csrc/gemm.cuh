@@ -36,11 +36,17 @@ struct GemmEpilogue {
   int in_rows_per_b;         // 0 = identity
   int out_rows_per_b;
   int out_row_off;
+  // split-K (GemmShape::splits > 1, fp32 flavour only): split 0 writes `out` (bias + residual as usual), split s > 0
+  // writes its raw partial product to split_out + (s - 1) * split_stride at the same [row, col] offsets; the consumer
+  // (the LayerNorm that follows, rowwise.cuh) adds the partials in a fixed order -> deterministic, no atomics
+  float* split_out;
+  long long split_stride;
 };
 
 struct GemmShape {
   int M, N, K;
   int stages;  // depth of the smem operand ring (2..GEMM_MAX_STAGES), chosen on the host from the grid size
+  int splits;  // K is cut into `splits` equal ranges, one CTA each (blockIdx.z = group * splits + split)
 };
 
 constexpr int GEMM_MAX_STAGES = 12;
@@ -70,7 +76,7 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_RELU = 2, EPI_F32 = 3 };
 //   EPI_F32    : out fp32 with the optional row remap into the [B, N, D] residual stream, bias, optional fp32 residual
 //                (same-row in-place residual, or a periodic table such as the positional embedding)
 
-static __device__ __noinline__ float4 gelu4(float4 v) {
+__device__ __forceinline__ float4 gelu4(float4 v) {
   v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   return v;
 }
@@ -96,8 +102,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * GEMM_BM;
-  const int g = blockIdx.z;
-  const int num_kb = shape.K / GEMM_BK;
+  const int g = blockIdx.z / shape.splits;
+  const int sp = blockIdx.z - g * shape.splits;
+  const int num_kb = shape.K / GEMM_BK / shape.splits;
+  const int kb0 = sp * num_kb;  // first k-block of this split
   const int pre = num_kb < STAGES ? num_kb : STAGES;  // k-blocks whose weight tile is requested before pdl_wait
   if (threadIdx.x == 0) TRACE_PT(0x100);
 
@@ -116,7 +124,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll 1
     for (int kb = 0; kb < pre; ++kb) {
       mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);  // A + W bytes; the A half is issued after pdl_wait
-      tma_load_3d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tma_w, &full_bar[kb], kb * GEMM_BK, n0, g);
+      tma_load_3d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tma_w, &full_bar[kb], (kb0 + kb) * GEMM_BK, n0, g);
     }
   }
   if (warp == 2) {
@@ -124,7 +132,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tmem_relinquish();
   }
   if (threadIdx.x >= 64 && threadIdx.x - 64 < BN)
-    s_bias[threadIdx.x - 64] = ep.bias ? __ldg(ep.bias + g * ep.bias_gstride + n0 + (threadIdx.x - 64)) : 0.0f;
+    s_bias[threadIdx.x - 64] = (ep.bias && sp == 0) ? __ldg(ep.bias + g * ep.bias_gstride + n0 + (threadIdx.x - 64)) : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,7 +147,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // ---------------- TMA producer ----------------
 #pragma unroll 1
       for (int kb = 0; kb < pre; ++kb)
-        tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], kb * GEMM_BK, m0, g);
+        tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
       int s = 0;              // pre == STAGES whenever the loop below runs
       uint32_t ph = 0;
 #pragma unroll 1
@@ -147,8 +155,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         mbar_wait(&empty_bar[s], ph);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        tma_load_3d(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
-        tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0, g);
+        tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
+        tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, g);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -288,14 +296,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               rr = per_rem;
               per_rem += RPI;
             }
-            r4[u] = (ep.resid && ok) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            r4[u] = (ep.resid && ok && sp == 0) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < UN; ++u) {
             if ((it0 + u) * RPI >= rows_left) continue;
             v[u].x += r4[u].x; v[u].y += r4[u].y; v[u].z += r4[u].z; v[u].w += r4[u].w;
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + g * ep.out_gstride + orow[u] * ep.out_ld + col) = v[u];
+            float* const obase = sp == 0 ? reinterpret_cast<float*>(ep.out) : ep.split_out + (sp - 1) * ep.split_stride;
+            *reinterpret_cast<float4*>(obase + g * ep.out_gstride + orow[u] * ep.out_ld + col) = v[u];
           }
         } else {
           __nv_bfloat16* const o = reinterpret_cast<__nv_bfloat16*>(ep.out) + g * ep.out_gstride + col;

@@ -85,8 +85,27 @@ int pick_bn(int M, int N, int groups) {
   return best;
 }
 
+int pick_splits(int M, int N, int K) {
+  // measured on B200 (tools/kernel_sweep.py): at M = 513 the K = 3072 GEMM takes 17 us unsplit (120 CTAs of 48
+  // k-blocks, L2 -> SM operand traffic bound) and about as long as a K = 768 GEMM when cut in four
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  if (N % 128 || K < 2048) return 1;
+  const int tiles = m_tiles * (N / 128);
+  int s = 1;
+  while (s < 4 && tiles * s * 2 <= 148 && K % (GEMM_BK * s * 2) == 0) s *= 2;
+  return s;
+}
+
 int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstride, const void* W, long long w_ld,
-                 long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep) {
+                 long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep, int splits) {
+  if (splits < 1) splits = 1;
+  if (splits > 1) {
+    if (!ep.out_f32 || !ep.split_out || K % (GEMM_BK * splits)) {
+      set_error("gemm: split-K needs an fp32 output, a partial buffer and K % (64 * splits) == 0");
+      return 1;
+    }
+    if (bn == 0) bn = 128;
+  }
   if (bn == 0) bn = pick_bn(M, N, groups);
   if (bn != 32 && bn != 64 && bn != 128) {
     set_error("gemm: N must be a multiple of 32");
@@ -111,11 +130,11 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     set_error("gemm: row remap / residual periods must be >= 8 rows");
     return 1;
   }
-  g->shape = GemmShape{M, N, K, 0};
+  g->shape = GemmShape{M, N, K, 0, splits};
   {
     // ring depth: ~100 KB so that two CTAs share an SM (epilogue / mainloop overlap, and PDL residency of the next kernel)
     const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA : GemmSmem<128>::STAGES_2CTA;
-    g->shape.stages = std::max(std::min(s2, K / GEMM_BK), 1);
+    g->shape.stages = std::max(std::min(s2, K / GEMM_BK / splits), 1);
   }
   g->ep = ep;
   g->bn = bn;
@@ -142,7 +161,7 @@ static void gemm_launch_bn(const GemmLaunch& g, dim3 grid, cudaStream_t stream) 
 }
 
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
-  dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups);
+  dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups * g.shape.splits);
   switch (g.bn) {
     case 32: gemm_launch_bn<32>(g, grid, stream); break;
     case 64: gemm_launch_bn<64>(g, grid, stream); break;

@@ -39,8 +39,12 @@ struct GemmLaunch {
 };
 
 // Builds the tensor maps for A [groups][M,K] and W [groups][N,K] (both bf16, K contiguous).
+// splits: 1 = no split-K; > 1 requires an fp32 output with ep.split_out set and K % (64 * splits) == 0.
 int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstride, const void* W, long long w_ld,
-                 long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep);
+                 long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep, int splits = 1);
+// split-K factor for an [M, N, K] fp32-output GEMM whose consumer can add partials: > 1 only when the unsplit grid
+// would leave most SMs idle (small M) and K is long
+int pick_splits(int M, int N, int K);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int pick_bn(int M, int N, int groups);
 

@@ -26,6 +26,12 @@ struct LnParams {
   const float* beta;
   float eps;
   int total_rows;      // B * rows
+  // split-K partial products of the GEMM that last updated these rows (gemm.cuh): added to the stream here, in a
+  // fixed order, and the sum is written back (same [B, N, D] offsets as x)
+  const float* partials;
+  int n_partials;
+  int partial_rows;        // only rows [0, partial_rows) of each sequence's range carry partials
+  long long partial_stride;
 };
 
 template <int NV>  // D = NV * 128  (768 -> 6, 1024 -> 8)
@@ -42,6 +48,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   float4 x[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) x[k] = *reinterpret_cast<const float4*>(src + k * 128 + lane * 4);
+  for (int sp = 0; sp < (i < p.partial_rows ? p.n_partials : 0); ++sp) {
+    const float* ps = p.partials + sp * p.partial_stride + (src - p.x);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(ps + k * 128 + lane * 4);
+      x[k].x += a.x; x[k].y += a.y; x[k].z += a.z; x[k].w += a.w;
+    }
+  }
   if (add) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -50,7 +64,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     }
   }
   float* dstf = src;
-  if (p.dst_mode == 1 && add) {
+  if ((p.dst_mode == 1 && add) || (p.n_partials > 0 && p.dst_mode != 2)) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(dstf + k * 128 + lane * 4) = x[k];
   }
