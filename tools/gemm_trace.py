@@ -29,9 +29,20 @@ with torch.cuda.stream(s):
 r = np.frombuffer(buf, dtype=np.uint64)[: 3 * n].reshape(n, 3)
 names = {0x100: "cta start", 0x101: "setup done", 0x102: "pdl wait passed", 0x103: "first stage landed",
          0x104: "last mma issued", 0x105: "accumulator ready", 0x106: "epilogue stored", 0x107: "teardown", 0x108: "stage1 done", 0x109: "first tmem ld done", 0x10a: "stage2 group0 loaded", 0x10b: "stage2 group0 stored"}
-t0 = int(r[:, 2].min())
+# records come in per-thread groups terminated by a (0xffff, clk_at_flush, ns_at_flush) marker: ns = ns_f - (clk_f - clk) / GHz
+GHZ = 1.9
+out_rows = []
+grp = []
+for tag, clk, ns in r.tolist():
+    if tag == 0xffff:
+        out_rows += [(t, c, ns - (clk - c) / GHZ) for t, c in grp]
+        grp = []
+    else:
+        grp.append((tag, clk))
+r = np.array(out_rows, dtype=np.float64).reshape(-1, 3)
+t0 = r[:, 2].min()
 order = np.argsort(r[:, 2], kind="stable")
 prev_clk = None
 for i in order:
-    tag, clk, ns = [int(v) for v in r[i]]
+    tag, clk, ns = int(r[i][0]), int(r[i][1]), r[i][2]
     print(f"{(ns - t0) / 1e3:9.2f} us  clk {clk % 10**9:10d}  {names.get(tag, hex(tag))}")

@@ -84,19 +84,35 @@ inline int g_pdl_enabled = [] {
 }();
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                            Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (g_pdl_enabled) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  return launch_kc(kernel, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -107,17 +123,32 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 struct TraceRec { unsigned long long tag, clk, ns; };
 static __device__ TraceRec g_trace[4096];
 static __device__ unsigned int g_trace_n;
-__device__ __forceinline__ void trace_pt(unsigned long long tag) {
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+// Low-overhead in-kernel timeline: a thread of CTA (0,0,0) collects (tag, clock64) pairs in a local array (a few
+// cycles per point) and flushes them once at the end with a single atomicAdd; ns is the global timer at the flush and
+// is back-computed per record on the host from the SM clock.
+struct TraceBuf {
+  unsigned long long tag[40], clk[40];
+  int n = 0;
+  __device__ __forceinline__ void pt(unsigned long long t) {
+    if (n < 40) { tag[n] = t; clk[n] = clock64(); ++n; }
+  }
+  __device__ __forceinline__ void flush() {
+    if (n == 0) return;
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-    const unsigned int i = atomicAdd(&g_trace_n, 1u);
-    if (i < 4096) { g_trace[i].tag = tag; g_trace[i].clk = clock64(); g_trace[i].ns = ns; }
+    const unsigned long long c_now = clock64();
+    const unsigned int base = atomicAdd(&g_trace_n, static_cast<unsigned int>(n) + 1u);
+    for (int i = 0; i < n && base + i < 4095; ++i) { g_trace[base + i].tag = tag[i]; g_trace[base + i].clk = clk[i]; g_trace[base + i].ns = 0; }
+    if (base + n < 4096) { g_trace[base + n].tag = 0xffff; g_trace[base + n].clk = c_now; g_trace[base + n].ns = ns; }
   }
-}
-#define TRACE_PT(tag) trace_pt(tag)
+};
+#define TRACE_DECL TraceBuf _tb; const bool _tb_on = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+#define TRACE_PT(tag) do { if (_tb_on) _tb.pt(tag); } while (0)
+#define TRACE_FLUSH() do { if (_tb_on) _tb.flush(); } while (0)
 #else
+#define TRACE_DECL ((void)0)
 #define TRACE_PT(tag) ((void)0)
+#define TRACE_FLUSH() ((void)0)
 #endif
 
 // ----------------------------------------------------------------------------------------------
@@ -187,6 +218,30 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each destination
+// CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMEM allocation
 // ----------------------------------------------------------------------------------------------
@@ -243,6 +298,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
 }
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
 // (implies tcgen05.fence::before_thread_sync)
+// same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (MMA_1sm + multicast TMA pipelines)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");

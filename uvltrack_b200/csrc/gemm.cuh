@@ -81,7 +81,11 @@ __device__ __forceinline__ float4 gelu4(float4 v) {
   return v;
 }
 
-template <int BN, int EPI>
+// MC (launched as clusters of two CTAs along N): the two CTAs compute neighbouring N tiles of the same M tile, so they
+// need the same A tile.  Each CTA fetches one 64-row half of it and TMA-multicasts the half into both CTAs' rings: the
+// L2 -> SM operand traffic, which bounds this kernel at every batch size (12 TB/s at 128x128 tiles), drops by a quarter.
+// A ring slot may be refilled only when BOTH CTAs have consumed it: the MMA commit arrives on both CTAs' empty barrier.
+template <int BN, int EPI, bool MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                     const GemmShape shape, const GemmEpilogue ep) {
@@ -107,6 +111,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_kb = shape.K / GEMM_BK / shape.splits;
   const int kb0 = sp * num_kb;  // first k-block of this split
   const int pre = num_kb < STAGES ? num_kb : STAGES;  // k-blocks whose weight tile is requested before pdl_wait
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  constexpr int A_HALF = S::A_BYTES / 2;
+  TRACE_DECL;
   if (threadIdx.x == 0) TRACE_PT(0x100);
 
   // ---- prologue: touches only weights (W tiles, bias), so under PDL it overlaps the predecessor kernel ----
@@ -117,7 +124,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll 1
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);
     }
     mbar_init(acc_bar, 1);
     fence_mbar_init();
@@ -135,6 +142,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     s_bias[threadIdx.x - 64] = (ep.bias && sp == 0) ? __ldg(ep.bias + g * ep.bias_gstride + n0 + (threadIdx.x - 64)) : 0.0f;
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers must be initialised before our multicast can signal them
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
   if (threadIdx.x == 0) TRACE_PT(0x101);
@@ -146,8 +154,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       // ---------------- TMA producer ----------------
 #pragma unroll 1
-      for (int kb = 0; kb < pre; ++kb)
-        tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
+      for (int kb = 0; kb < pre; ++kb) {
+        if (MC)
+          tma_load_3d_mc(smem + kb * S::STAGE_BYTES + crank * A_HALF, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK,
+                         m0 + crank * (GEMM_BM / 2), g, 0x3);
+        else
+          tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
+      }
       int s = 0;              // pre == STAGES whenever the loop below runs
       uint32_t ph = 0;
 #pragma unroll 1
@@ -155,7 +168,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         mbar_wait(&empty_bar[s], ph);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
+        if (MC)
+          tma_load_3d_mc(a_dst + crank * A_HALF, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0 + crank * (GEMM_BM / 2), g,
+                         0x3);
+        else
+          tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
         tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, g);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -180,7 +197,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
           umma_bf16_ss(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have drained
+        // frees the smem slot (in both CTAs of the cluster) when these MMAs have drained
+        if (MC) umma_commit_mc(&empty_bar[s], 0x3);
+        else umma_commit(&empty_bar[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(acc_bar);  // accumulator complete
@@ -320,11 +339,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
 
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's last commits / multicasts target this CTA's shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, TMEM_COLS);
   }
   if (threadIdx.x == 64) TRACE_PT(0x107);
+  if (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64) TRACE_FLUSH();
 }
 
 }  // namespace uvlt

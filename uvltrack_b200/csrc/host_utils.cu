@@ -56,8 +56,10 @@ int init_kernel_attributes() {
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   if (status == 0) return 0;
-#define UVLT_GEMM_ATTR(BN, EPI)                                                                              \
-  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define UVLT_GEMM_ATTR(BN, EPI)                                                                                     \
+  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    GemmSmem<BN>::total(GemmSmem<BN>::STAGES_2CTA)));                                 \
+  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                     GemmSmem<BN>::total(GemmSmem<BN>::STAGES_2CTA)))
 #define UVLT_GEMM_ATTR_BN(BN) \
   UVLT_GEMM_ATTR(BN, EPI_BF16); UVLT_GEMM_ATTR(BN, EPI_BF16_GELU); UVLT_GEMM_ATTR(BN, EPI_BF16_RELU); UVLT_GEMM_ATTR(BN, EPI_F32)
@@ -70,6 +72,14 @@ int init_kernel_attributes() {
   status = 0;
   return 0;
 }
+
+// Off by default: measured on B200 (profiles/r01_gemm_multicast.txt) the cluster variant is 5-20 % SLOWER at every
+// batch size -- the L2 already merges the two CTAs' near-simultaneous requests for the same A tile, so multicast saves no
+// L2 bandwidth and only adds the cross-CTA slot handshake.  UVLT_MULTICAST=1 enables it for experiments.
+int g_gemm_multicast = [] {
+  const char* e = getenv("UVLT_MULTICAST");
+  return (e && e[0] == '1') ? 1 : 0;
+}();
 
 int pick_bn(int M, int N, int groups) {
   // Widest tile that still gives one CTA per SM (148) (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
@@ -141,31 +151,44 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   g->groups = groups;
   if (groups == 1) { a_gstride = static_cast<long long>(M) * a_ld; w_gstride = static_cast<long long>(N) * w_ld; }
   if (make_tma_bf16_3d(&g->tma_a, A, K, M, groups, a_ld * 2, a_gstride * 2, GEMM_BM)) return 1;
+  // pairs of CTAs along N share the A tile through TMA multicast (64-row halves) whenever the N tiles pair up
+  g->multicast = g_gemm_multicast && ((N / bn) % 2 == 0);
+  if (g->multicast && make_tma_bf16_3d(&g->tma_a_half, A, K, M, groups, a_ld * 2, a_gstride * 2, GEMM_BM / 2)) return 1;
   if (make_tma_bf16_3d(&g->tma_w, W, K, N, groups, w_ld * 2, w_gstride * 2, bn)) return 1;
   return 0;
 }
 
-template <int BN>
+template <int BN, bool MC>
 static void gemm_launch_bn(const GemmLaunch& g, dim3 grid, cudaStream_t stream) {
   const size_t smem = GemmSmem<BN>::total(g.shape.stages);
   const dim3 block(GEMM_THREADS);
+  const CUtensorMap& ta = MC ? g.tma_a_half : g.tma_a;
+  const int cl = MC ? 2 : 1;
   if (g.ep.out_f32) {
-    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_F32>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+    (void)launch_kc(gemm_bf16_tn_kernel<BN, EPI_F32, MC>, grid, block, smem, stream, cl, ta, g.tma_w, g.shape, g.ep);
   } else if (g.ep.act == ACT_GELU) {
-    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16_GELU>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+    (void)launch_kc(gemm_bf16_tn_kernel<BN, EPI_BF16_GELU, MC>, grid, block, smem, stream, cl, ta, g.tma_w, g.shape, g.ep);
   } else if (g.ep.act == ACT_RELU) {
-    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16_RELU>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+    (void)launch_kc(gemm_bf16_tn_kernel<BN, EPI_BF16_RELU, MC>, grid, block, smem, stream, cl, ta, g.tma_w, g.shape, g.ep);
   } else {
-    UVLT_LAUNCH((gemm_bf16_tn_kernel<BN, EPI_BF16>), grid, block, smem, stream, g.tma_a, g.tma_w, g.shape, g.ep);
+    (void)launch_kc(gemm_bf16_tn_kernel<BN, EPI_BF16, MC>, grid, block, smem, stream, cl, ta, g.tma_w, g.shape, g.ep);
   }
 }
 
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
   dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups * g.shape.splits);
-  switch (g.bn) {
-    case 32: gemm_launch_bn<32>(g, grid, stream); break;
-    case 64: gemm_launch_bn<64>(g, grid, stream); break;
-    default: gemm_launch_bn<128>(g, grid, stream); break;
+  if (g.multicast) {
+    switch (g.bn) {
+      case 32: gemm_launch_bn<32, true>(g, grid, stream); break;
+      case 64: gemm_launch_bn<64, true>(g, grid, stream); break;
+      default: gemm_launch_bn<128, true>(g, grid, stream); break;
+    }
+  } else {
+    switch (g.bn) {
+      case 32: gemm_launch_bn<32, false>(g, grid, stream); break;
+      case 64: gemm_launch_bn<64, false>(g, grid, stream); break;
+      default: gemm_launch_bn<128, false>(g, grid, stream); break;
+    }
   }
   UVLT_CUDA_OK(cudaGetLastError());
   return 0;

@@ -32,6 +32,8 @@ int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
 
 struct GemmLaunch {
   CUtensorMap tma_a, tma_w;
+  CUtensorMap tma_a_half;  // 64-row boxes of A for the multicast variant
+  bool multicast;
   GemmShape shape;
   GemmEpilogue ep;
   int bn;      // 32 / 64 / 128
@@ -47,6 +49,7 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
 int pick_splits(int M, int N, int K);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int pick_bn(int M, int N, int groups);
+extern int g_gemm_multicast;  // UVLT_MULTICAST=0 disables the cluster / TMA-multicast GEMM variant
 
 struct AttnLaunch {
   CUtensorMap tma_qkv;
