@@ -6,13 +6,13 @@ set -u
 TAG=$1; shift
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
-# every kernel of 2 timed steps (after warm-up launches are skipped by bench's own warm-up: we keep them all and filter here)
-timeout 600 $NCU --metrics gpu__time_duration.sum -c 1200 --csv --log-file gpurun_out/${TAG}_launches.csv \
+timeout 600 $NCU --metrics gpu__time_duration.sum -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_launches.log 2>&1
 echo "launch list rc=$?"
-timeout 600 $NCU --set full --import-source on -k regex:gemm_bf16 -s 200 -c 4 -f -o gpurun_out/${TAG}_gemm \
+# the four layer GEMMs of a middle layer (skip the first ~300 GEMM launches: init + warm-up)
+timeout 600 $NCU --set full --import-source on -k regex:gemm_bf16 -s 300 -c 4 -f -o gpurun_out/${TAG}_gemm \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_gemm.log 2>&1
 echo "gemm capture rc=$?"
-timeout 600 $NCU --set full --import-source on -k regex:attention_kernel -s 40 -c 2 -f -o gpurun_out/${TAG}_attn \
+timeout 600 $NCU --set full --import-source on -k regex:attention_kernel -s 60 -c 2 -f -o gpurun_out/${TAG}_attn \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_attn.log 2>&1
 echo "attn capture rc=$?"
