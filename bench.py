@@ -188,13 +188,21 @@ def kernel_rooflines(dims, B, skip_text, pk):
     ta = timed(afn)
     fa = 4.0 * B * H * n * n * 64
     peak = pk["bf16_tflops"]
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the four layer shapes) from the
+    # committed `ncu --set full` captures of these very launches: profiles/r01_final_b1_gemm_full.md (M = 513);
+    # other shapes have no committed capture -> null
+    traffic = {513: round((4.353 + 3.569 + 5.552 + 9.474) / 4 * 1e6)}.get(M)
     roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (qkv+proj+fc1+fc2 of one layer, M=%d)" % M,
             "achieved": round(g_flops / g_time / 1e12, 2), "peak": peak, "unit": "TFLOP/s",
-            "frac": round(g_flops / g_time / 1e12 / peak, 4), "traffic": None, "peak_source": pk["source"] + " (burst)",
+            "frac": round(g_flops / g_time / 1e12 / peak, 4), "traffic": traffic,
+            "traffic_note": "mean DRAM bytes per launch, ncu --set full (profiles/r01_final_b1_gemm_full.md); "
+                            "algorithmic weight bytes per launch: %d" % round((3 * D * D + D * D + 2 * D * Hd) * 2 / 4),
+            "peak_source": pk["source"] + " (burst)",
             "per_shape": per, "avg_launch_us": round(g_time / 4 * 1e6, 2)}
     roof_a = {"bound": "tensor", "kernel": "attention_kernel (B=%d, H=%d, n=%d)" % (B, H, n),
               "achieved": round(fa / ta / 1e12, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(fa / ta / 1e12 / peak, 4),
-              "traffic": None, "avg_launch_us": round(ta * 1e6, 2)}
+              "traffic": {(1, 513): 2439424}.get((B, n)), "traffic_note": "ncu --set full, profiles/r01_final_b1_attn_full.md",
+              "avg_launch_us": round(ta * 1e6, 2)}
     return roof, roof_a
 
 
