@@ -64,7 +64,7 @@ def peaks():
 
 def workload_name(a):
     return (f"UVLTrack-{'B' if a.arch == 'base' else 'L'} baseline_{a.arch} template {a.template_size}^2 / search "
-            f"{a.search_size}^2 / 40-token text, {a.mode} mode, batch={a.batch} per GPU, synthetic {a.steps}-frame sequence")
+            f"{a.search_size}^2 / 40-token text, {a.mode} mode, batch={a.batch} per GPU, synthetic sequence")
 
 
 class ClockSampler:
