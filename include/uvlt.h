@@ -101,6 +101,16 @@ typedef struct uvlt_outputs {
                               (modality_unified_feature_extractor.py:47), so the BERT branch and the text rows are
                               not evaluated; `tokens` text rows are then undefined.  Image-side results are identical. */
 
+#define UVLT_TEXT_CACHED 4 /* the text rows entering the first fusion layer were computed by uvlt_text_encode for these
+                              sequences (ids / text_mask are constant per sequence): the BERT embedding and the
+                              BERT-only layers are not re-run, their rows are restored from the cache.  Bit-identical. */
+
+/* BertModel.embedding + the first min(FUSION_LAYER) BertLayers (bert_backbone.py:740-750, :383-394) for `batch`
+ * sequences, once per sequence (Tracker.initialize); fills the engine's text cache used by UVLT_TEXT_CACHED
+ * (SURVEY 8f row n4).  ids int64 [B,T], text_mask fp32 [B,T], flag int64 [B]: device pointers. */
+UVLT_API int uvlt_text_encode(uvlt_handle h, const int64_t* ids, const float* text_mask, const int64_t* flag,
+                              int32_t batch, void* stream);
+
 /* UVLTrack.forward_test (lib/models/uvltrack/uvltrack.py:41-45).
  *   template [B,3,Hz,Hz] fp32, search [B,3,Hx,Hx] fp32, ids int64 [B,T], text_mask fp32 [B,T] (1 = real token),
  *   prompt fp32 [B,3,D], flag int64 [B] (0 BBOX, 1 NL, 2 NL+BBOX) -- all DEVICE pointers. */

@@ -138,6 +138,25 @@ def test_skip_text_is_exact_in_bbox_mode(case):
     assert model.engine.last_launch_count < 120
 
 
+def test_text_cache_is_exact(case):
+    """the BERT-only layers depend on the (constant) text alone; running them once
+    (uvlt_text_encode) and restoring their rows every frame must not change a single bit."""
+    g, meta, dims, inp, model = case
+    if meta["mode"] == "BBOX":
+        pytest.skip("no text branch in BBOX mode")
+    text = NestedTensor(T(inp["ids"]), T(inp["text_mask"]))
+    args = (T(inp["template"]), T(inp["search"]), text, T(inp["prompt"]), T(inp["flag"]))
+    full = model.engine.forward_test(*args)
+    n_full = model.engine.last_launch_count
+    model.engine.text_encode(text, T(inp["flag"]))
+    fast = model.engine.forward_test(*args, text_cached=True)
+    assert model.engine.last_launch_count < n_full - 30   # embedding + 6 x 7 BERT kernels are gone
+    for k in ("cls_score_test", "bbox_map", "cont_score", "pred_boxes", "tokens"):
+        assert torch.equal(full[k], fast[k]), k
+    with pytest.raises(RuntimeError):
+        model.engine.forward_test(*args, text_cached=True, want_logits=True)
+
+
 def test_batch_independence_and_order(case):
     """Sequences never interact: sequence b of a batch equals the same sequence run alone, bit for bit,
     and permuting the batch permutes the outputs."""

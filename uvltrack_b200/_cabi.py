@@ -43,6 +43,7 @@ class UvltOutputs(C.Structure):
 
 WANT_LOGITS = 1
 SKIP_TEXT = 2
+TEXT_CACHED = 4
 
 _P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/uvlt.h declares (tests/test_cabi_symbols.py checks)
@@ -63,6 +64,7 @@ SIGNATURES = {
     "uvlt_track_frame_image_host": (c_int, [_P, _P, c_int32, c_int32, _P, C.c_double, _P, _P, _P, _P, _P, _P, c_int32,
                                             c_int32, c_int32, _P, _P, _P, _P]),
     "uvlt_op_crop_resize": (c_int, [_P, c_int32, c_int32, _P, C.c_double, c_int32, _P, _P, c_int32, _P]),
+    "uvlt_text_encode": (c_int, [_P, _P, _P, _P, c_int32, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,

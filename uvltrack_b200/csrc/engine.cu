@@ -51,6 +51,7 @@ struct LayerPlan {
 struct Plan {
   int B = 0;
   bool skip_text = false;
+  bool text_cached = false;  // the BERT branch was run once per sequence (uvlt_text_encode); its rows are restored
   GemmLaunch patch;
   std::vector<LayerPlan> vit;   // depth
   std::vector<LayerPlan> bert;  // fusion_start
@@ -98,6 +99,8 @@ struct uvlt_engine {
   // activations
   float* x = nullptr;
   float* xpart = nullptr;  // [3][B, N, D] split-K partial products of fc2 (same offsets as x)
+  float* text_cache = nullptr;  // [B, T, D] text rows after the last BERT-only layer (constant per sequence)
+  int text_cache_batch = 0;
   __nv_bfloat16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *pcol = nullptr;
   __nv_bfloat16 *t_a = nullptr, *t_qkv = nullptr, *t_att = nullptr, *t_hid = nullptr;
   float *bias_vis = nullptr, *bias_joint = nullptr, *bias_bert = nullptr;
@@ -148,7 +151,7 @@ int alloc_activations(uvlt_engine* e) {
   const size_t B = e->Bm, N = e->N, D = e->D, Hd = e->Hd, T = e->T, SS = e->SS, C = e->C;
   if (dalloc(e, &e->x, B * N * D)) return 1;
   ENG_CUDA(cudaMemset(e->x, 0, B * N * D * sizeof(float)));
-  if (dalloc(e, &e->xpart, 3 * B * N * D)) return 1;
+  if (dalloc(e, &e->xpart, 3 * B * N * D) || dalloc(e, &e->text_cache, B * T * D)) return 1;
   if (dalloc(e, &e->a, B * N * D) || dalloc(e, &e->qkv, B * N * 3 * D) || dalloc(e, &e->att, B * N * D) ||
       dalloc(e, &e->hid, B * N * Hd) || dalloc(e, &e->pcol, B * (e->Nz + e->Nx) * 768))
     return 1;
@@ -389,8 +392,8 @@ GemmEpilogue ep_stream(uvlt_engine* e, const float* bias, int rows, int row_off)
 
 // `exact_stream`: the token stream must be complete after every layer (per-layer contrastive logits read it), so fc2 is
 // not split
-Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false) {
-  const int key = B * 4 + (skip_text ? 2 : 0) + (exact_stream ? 1 : 0);
+Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false, bool text_cached = false) {
+  const int key = B * 8 + (skip_text ? 4 : 0) + (exact_stream ? 2 : 0) + (text_cached ? 1 : 0);
   auto it = e->plans.find(key);
   if (it != e->plans.end()) return it->second.get();
   auto plan = std::make_unique<Plan>();
@@ -398,6 +401,7 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false)
   p->B = B;
   p->skip_text = skip_text;
   p->exact_stream = exact_stream;
+  p->text_cached = text_cached;
   const int D = e->D, Hd = e->Hd, Nv = e->Nv, N = e->N, T = e->T;
   {
     GemmEpilogue ep{};
@@ -589,7 +593,7 @@ int vit_layer(uvlt_engine* e, Plan* p, cudaStream_t s, int i) {
 int run_layers(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits) {
   RUN(gemm_launch(p->patch, s));
   const bool text = !p->skip_text;
-  const bool fork = text && e->F0 > 0 && !want_logits;
+  const bool fork = text && e->F0 > 0 && !want_logits && !p->text_cached;
   if (want_logits && !text) {
     set_error("UVLT_WANT_LOGITS cannot be combined with UVLT_SKIP_TEXT");
     return 1;
@@ -608,8 +612,14 @@ int run_layers(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits) {
       ENG_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
       joined = true;
     }
+    if (i == e->F0 && text && p->text_cached) {
+      // text rows as the BERT-only layers left them: constant per sequence, computed once by uvlt_text_encode
+      const size_t row_bytes = static_cast<size_t>(e->T) * e->D * sizeof(float);
+      ENG_CUDA(cudaMemcpy2DAsync(e->x + static_cast<size_t>(e->Nv) * e->D, static_cast<size_t>(e->N) * e->D * sizeof(float),
+                                 e->text_cache, row_bytes, row_bytes, p->B, cudaMemcpyDeviceToDevice, s));
+    }
     if (vit_layer(e, p, s, i)) return 1;
-    if (text && !fork && i < e->F0 && bert_layer(e, p, s, i)) return 1;
+    if (text && !fork && !p->text_cached && i < e->F0 && bert_layer(e, p, s, i)) return 1;
     if (want_logits) {
       bool is_cont = false;
       for (int k = 0; k < e->cfg.num_cont_layers; ++k) is_cont |= (e->cfg.cont_layers[k] == i);
@@ -690,11 +700,13 @@ int run_prompter(uvlt_engine* e, Plan* p, cudaStream_t s, const float* tokens, c
 
 int stage_inputs(uvlt_engine* e, cudaStream_t s, int B, const float* tmpl, const float* search, const uint8_t* search_u8,
                  const long long* ids, const float* text_mask, const float* prompt, const long long* flag,
-                 bool skip_text) {
-  PatchParams pp{tmpl, nullptr, search, search_u8, B, e->Hz, e->Hx, e->pcol, e->cls_tok, e->x,
-                 static_cast<long long>(e->N) * e->D, e->D};
-  if (launch_patch_im2col(pp, s)) { set_error("patch_im2col launch failed"); return 1; }
-  ++e->launch_count;
+                 bool skip_text, bool images = true) {
+  if (images) {
+    PatchParams pp{tmpl, nullptr, search, search_u8, B, e->Hz, e->Hx, e->pcol, e->cls_tok, e->x,
+                   static_cast<long long>(e->N) * e->D, e->D};
+    if (launch_patch_im2col(pp, s)) { set_error("patch_im2col launch failed"); return 1; }
+    ++e->launch_count;
+  }
   BiasParams bp{flag, text_mask, B, e->Nz, e->Nx, e->T, e->bias_vis, e->bias_joint, e->bias_bert,
                 e->flag_d, e->mask_d, prompt, e->prompt_d, B * 3 * e->D};
   if (launch_build_bias(bp, s)) { set_error("build_bias launch failed"); return 1; }
@@ -740,6 +752,13 @@ int run_core(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits, bool wit
   }
   ENG_CUDA(cudaGraphLaunch(p->graph[gi], s));
   e->launch_count += p->graph_kernels[gi];
+  return 0;
+}
+
+int check_text_cache(uvlt_engine* e, int B, bool cached, bool logits) {
+  if (!cached) return 0;
+  if (logits) { set_error("UVLT_TEXT_CACHED cannot be combined with UVLT_WANT_LOGITS (per-layer text tokens are needed)"); return 1; }
+  if (e->text_cache_batch < B) { set_error("UVLT_TEXT_CACHED: call uvlt_text_encode for this batch first"); return 1; }
   return 0;
 }
 
@@ -924,11 +943,13 @@ int uvlt_forward_test(uvlt_handle e, const float* tmpl, const float* search, con
   if (!tmpl || !search || !ids || !text_mask || !prompt || !flag) { set_error("uvlt_forward_test: null input"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool skip_text = flags & UVLT_SKIP_TEXT, logits = flags & UVLT_WANT_LOGITS;
-  Plan* p = get_plan(e, B, skip_text, logits);
+  const bool cached = (flags & UVLT_TEXT_CACHED) && !skip_text;
+  if (check_text_cache(e, B, cached, logits)) return 1;
+  Plan* p = get_plan(e, B, skip_text, logits, cached);
   if (!p) return 1;
   e->launch_count = 0;
   if (stage_inputs(e, s, B, tmpl, search, nullptr, reinterpret_cast<const long long*>(ids), text_mask, prompt,
-                   reinterpret_cast<const long long*>(flag), skip_text))
+                   reinterpret_cast<const long long*>(flag), skip_text || cached))
     return 1;
   if (run_core(e, p, s, logits, true)) return 1;
   e->last_B = B;
@@ -1017,13 +1038,15 @@ int uvlt_track_frame_host(uvlt_handle e, const uint8_t* search_u8_host, const fl
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool skip_text = flags & UVLT_SKIP_TEXT;
-  Plan* p = get_plan(e, B, skip_text);
+  const bool cached = (flags & UVLT_TEXT_CACHED) && !skip_text;
+  if (check_text_cache(e, B, cached, false)) return 1;
+  Plan* p = get_plan(e, B, skip_text, false, cached);
   if (!p) return 1;
   e->launch_count = 0;
   const size_t bytes = static_cast<size_t>(B) * e->Hx * e->Hx * 3;
   ENG_CUDA(cudaMemcpyAsync(e->u8_stage, search_u8_host, bytes, cudaMemcpyHostToDevice, s));
   if (stage_inputs(e, s, B, tmpl, nullptr, e->u8_stage, reinterpret_cast<const long long*>(ids), text_mask, prompt,
-                   reinterpret_cast<const long long*>(flag), skip_text))
+                   reinterpret_cast<const long long*>(flag), skip_text || cached))
     return 1;
   if (run_core(e, p, s, false, true)) return 1;
   e->last_B = B;
@@ -1051,7 +1074,9 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool skip_text = flags & UVLT_SKIP_TEXT;
-  Plan* p = get_plan(e, B, skip_text);
+  const bool cached = (flags & UVLT_TEXT_CACHED) && !skip_text;
+  if (check_text_cache(e, B, cached, false)) return 1;
+  Plan* p = get_plan(e, B, skip_text, false, cached);
   if (!p) return 1;
   e->launch_count = 0;
   const size_t bytes = static_cast<size_t>(B) * frame_h * frame_w * 3;
@@ -1069,7 +1094,7 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
   if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
   ++e->launch_count;
   if (stage_inputs(e, s, B, tmpl, nullptr, e->u8_stage, reinterpret_cast<const long long*>(ids), text_mask, prompt,
-                   reinterpret_cast<const long long*>(flag), skip_text))
+                   reinterpret_cast<const long long*>(flag), skip_text || cached))
     return 1;
   if (run_core(e, p, s, false, true)) return 1;
   e->last_B = B;
@@ -1090,6 +1115,27 @@ int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w,
   UVLT_LAUNCH(crop_resize_kernel, dim3((out_size * out_size + 255) / 256, B), dim3(256), 0,
               static_cast<cudaStream_t>(stream), cp);
   if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
+  return 0;
+}
+
+int uvlt_text_encode(uvlt_handle e, const int64_t* ids, const float* text_mask, const int64_t* flag, int32_t B,
+                     void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!ids || !text_mask || !flag) { set_error("uvlt_text_encode: null input"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan* p = get_plan(e, B, false);
+  if (!p) return 1;
+  e->launch_count = 0;
+  if (stage_inputs(e, s, B, nullptr, nullptr, nullptr, reinterpret_cast<const long long*>(ids), text_mask, nullptr,
+                   reinterpret_cast<const long long*>(flag), false, /*images=*/false))
+    return 1;
+  for (int i = 0; i < e->F0; ++i)
+    if (bert_layer(e, p, s, i)) return 1;
+  const size_t row_bytes = static_cast<size_t>(e->T) * e->D * sizeof(float);
+  ENG_CUDA(cudaMemcpy2DAsync(e->text_cache, row_bytes, e->x + static_cast<size_t>(e->Nv) * e->D,
+                             static_cast<size_t>(e->N) * e->D * sizeof(float), row_bytes, B, cudaMemcpyDeviceToDevice, s));
+  e->text_cache_batch = B;
   return 0;
 }
 

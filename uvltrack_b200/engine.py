@@ -153,7 +153,17 @@ class Engine:
         return res["text"][:, :1]
 
     # ------------------------------------------------------------------------------------------------------
-    def forward_test(self, template, search, text, prompt, flag, want_logits=False, skip_text=False, clone=True):
+    def text_encode(self, text, flag):
+        """BERT embedding + BERT-only layers once per sequence (constant text): fills the engine's text cache that
+        ``text_cached=True`` forwards restore instead of re-running the branch every frame."""
+        B = text.tensors.shape[0]
+        ids, mask, fl = self._prep_text(text, flag, B)
+        _cabi.check(self.lib.uvlt_text_encode(self.h, _cabi.ptr(ids), _cabi.ptr(mask), _cabi.ptr(fl), B,
+                                              _cabi.current_stream()), "uvlt_text_encode")
+        self._text_owner = None  # whoever relies on the cache re-claims it (BatchTracker does)
+
+    def forward_test(self, template, search, text, prompt, flag, want_logits=False, skip_text=False, clone=True,
+                     text_cached=False):
         """UVLTrack.forward_test (lib/models/uvltrack/uvltrack.py:41-45)."""
         import torch
 
@@ -161,7 +171,8 @@ class Engine:
         tmpl, srch, prompt = self._f32(template), self._f32(search), self._f32(prompt)
         ids, mask, fl = self._prep_text(text, flag, B)
         out = _cabi.UvltOutputs()
-        flags = (_cabi.WANT_LOGITS if want_logits else 0) | (_cabi.SKIP_TEXT if skip_text else 0)
+        flags = ((_cabi.WANT_LOGITS if want_logits else 0) | (_cabi.SKIP_TEXT if skip_text else 0) |
+                 (_cabi.TEXT_CACHED if text_cached else 0))
         _cabi.check(self.lib.uvlt_forward_test(self.h, _cabi.ptr(tmpl), _cabi.ptr(srch), _cabi.ptr(ids), _cabi.ptr(mask),
                                                _cabi.ptr(prompt), _cabi.ptr(fl), B, flags, C.byref(out),
                                                _cabi.current_stream()), "uvlt_forward_test")
@@ -234,17 +245,19 @@ class Engine:
         return out
 
     def track_frame_host(self, search_u8_pinned, template, ids, text_mask, prompt, flag, window, out_pinned, batch,
-                         has_cont=True, skip_text=False, max_score=None, snapshot=None):
+                         has_cont=True, skip_text=False, max_score=None, snapshot=None, text_cached=False):
         """One tracker step from pinned host memory (uint8 crops in, [B,6] rows out); synchronises the stream."""
         _cabi.check(self.lib.uvlt_track_frame_host(
             self.h, C.c_void_p(search_u8_pinned.data_ptr()), _cabi.ptr(template), _cabi.ptr(ids), _cabi.ptr(text_mask),
-            _cabi.ptr(prompt), _cabi.ptr(flag), _cabi.ptr(window), int(batch), _cabi.SKIP_TEXT if skip_text else 0,
+            _cabi.ptr(prompt), _cabi.ptr(flag), _cabi.ptr(window), int(batch),
+            (_cabi.SKIP_TEXT if skip_text else 0) | (_cabi.TEXT_CACHED if text_cached else 0),
             int(has_cont), _cabi.ptr(max_score), _cabi.ptr(snapshot), C.c_void_p(out_pinned.data_ptr()),
             _cabi.current_stream()), "uvlt_track_frame_host")
         return out_pinned
 
     def track_frame_image_host(self, frames_pinned, state_dev, search_factor, template, ids, text_mask, prompt, flag,
-                               window, out_pinned, batch, has_cont=True, skip_text=False, max_score=None, snapshot=None):
+                               window, out_pinned, batch, has_cont=True, skip_text=False, max_score=None, snapshot=None,
+                               text_cached=False):
         """One tracker step from the raw frames (pinned uint8 [B,H,W,3]): crop + resize, forward, merge and box update
         all on the device; ``state_dev`` (fp64 [B,4]) is updated in place, ``out_pinned`` (fp64 [B,10]) receives the rows.
         Synchronises the stream."""
@@ -252,6 +265,7 @@ class Engine:
         _cabi.check(self.lib.uvlt_track_frame_image_host(
             self.h, C.c_void_p(frames_pinned.data_ptr()), int(H), int(W), _cabi.ptr(state_dev), float(search_factor),
             _cabi.ptr(template), _cabi.ptr(ids), _cabi.ptr(text_mask), _cabi.ptr(prompt), _cabi.ptr(flag),
-            _cabi.ptr(window), int(batch), _cabi.SKIP_TEXT if skip_text else 0, int(has_cont), _cabi.ptr(max_score),
-            _cabi.ptr(snapshot), C.c_void_p(out_pinned.data_ptr()), _cabi.current_stream()), "uvlt_track_frame_image_host")
+            _cabi.ptr(window), int(batch), (_cabi.SKIP_TEXT if skip_text else 0) | (_cabi.TEXT_CACHED if text_cached else 0),
+            int(has_cont), _cabi.ptr(max_score), _cabi.ptr(snapshot), C.c_void_p(out_pinned.data_ptr()),
+            _cabi.current_stream()), "uvlt_track_frame_image_host")
         return out_pinned

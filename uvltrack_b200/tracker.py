@@ -97,6 +97,8 @@ class BatchTracker:
         # device_preprocess: crop / resize / box update on the GPU (uvlt_track_frame_image_host); False keeps the
         # reference's host pre/post-processing (OpenCV) around uvlt_track_frame_host.  Same boxes either way.
         self.device_preprocess = bool(device_preprocess)
+        self.cache_text = bool(getattr(params, "cache_text", True))
+        self.text_cached = False
         self.params = params
         self.cfg = params.cfg
         self.B = int(batch)
@@ -221,6 +223,12 @@ class BatchTracker:
         self.state_dev.copy_(torch.tensor([[float(v) for v in st] for st in self.state], dtype=torch.float64))
         self.skip_text = bool((flags == 0).all())
         text = NestedTensor(self.ids, self.text_mask)
+        # the language branch before the first fusion layer depends only on the (constant) text: run it once here and
+        # let every frame restore its rows (identical results)
+        self.text_cached = self.cache_text and not self.skip_text
+        if self.text_cached:
+            self.engine.text_encode(text, self.flag)
+            self.engine._text_owner = self  # the cache lives in the engine: another tracker on it may overwrite it
         self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx.cuda(), text, self.template_mask,
                                                            torch.from_numpy(ctx_mask).cuda(), self.flag))
         self.frame_id = 0
@@ -233,6 +241,9 @@ class BatchTracker:
         self.frame_id += 1
         S = self.params.search_size
         results, update = [], []
+        if self.text_cached and getattr(self.engine, "_text_owner", None) is not self:
+            self.engine.text_encode(NestedTensor(self.ids, self.text_mask), self.flag)
+            self.engine._text_owner = self
         shapes = {im.shape for im in images}
         if self.device_preprocess and len(shapes) == 1 and images[0].dtype == np.uint8 and images[0].ndim == 3:
             # ---- everything but the frame upload on the device ----
@@ -245,7 +256,8 @@ class BatchTracker:
             self.engine.track_frame_image_host(self.frames, self.state_dev, self.params.search_factor, self.template,
                                                self.ids, self.text_mask, self.prompt, self.flag, self.window_dev,
                                                self.out10, self.B, has_cont=self.has_cont, skip_text=self.skip_text,
-                                               max_score=self.max_score_dev, snapshot=self.snapshot)
+                                               max_score=self.max_score_dev, snapshot=self.snapshot,
+                                               text_cached=self.text_cached)
             rows = []
             for b in range(self.B):
                 row = self.out10_np[b]
@@ -262,7 +274,8 @@ class BatchTracker:
                 self.crops_np[b] = crop
             self.engine.track_frame_host(self.crops, self.template, self.ids, self.text_mask, self.prompt, self.flag,
                                          self.window_dev, self.out, self.B, has_cont=self.has_cont,
-                                         skip_text=self.skip_text, max_score=self.max_score_dev, snapshot=self.snapshot)
+                                         skip_text=self.skip_text, max_score=self.max_score_dev, snapshot=self.snapshot,
+                                         text_cached=self.text_cached)
             rows = []
             for b, image in enumerate(images):
                 H, W = image.shape[:2]
