@@ -175,6 +175,13 @@ UVLT_API int uvlt_track_frame_image_host(uvlt_handle h, const uint8_t* frames_ho
                                          const double* window, int32_t batch, int32_t flags, int32_t has_cont,
                                          float* max_score, float* snapshot, double* out_host, void* stream);
 
+/* Asynchronous piecewise upload of the raw frames of the next uvlt_track_frame_image_host call (which is then given
+ * frames_host == NULL): `nbytes` from `host` (pinned recommended) to byte offset `dst_offset` of the engine's
+ * [B, frame_h, frame_w, 3] staging buffer of `total_bytes`.  Lets the caller overlap its host-side staging copies with
+ * the DMA, piece by piece.  Enqueued on `stream`; no synchronisation (except when the buffer has to grow). */
+UVLT_API int uvlt_upload_frames(uvlt_handle h, const uint8_t* host, int64_t dst_offset, int64_t nbytes,
+                                int64_t total_bytes, void* stream);
+
 /* sample_target alone (device pointers): frames uint8 [B,H,W,3], state fp64 [B,4] -> crops uint8 [B,S,S,3] and
  * resize_factor fp64 [B] (0 when the crop side is < 1). */
 UVLT_API int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, const double* state,

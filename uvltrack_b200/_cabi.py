@@ -65,6 +65,7 @@ SIGNATURES = {
                                             c_int32, c_int32, _P, _P, _P, _P]),
     "uvlt_op_crop_resize": (c_int, [_P, c_int32, c_int32, _P, C.c_double, c_int32, _P, _P, c_int32, _P]),
     "uvlt_text_encode": (c_int, [_P, _P, _P, _P, c_int32, _P]),
+    "uvlt_upload_frames": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -117,6 +118,7 @@ struct uvlt_engine {
   // device-resident tracker step (track.cuh)
   uint8_t* frame_stage = nullptr;  // [B, H, W, 3] staging of the raw frames, grown on demand
   size_t frame_stage_bytes = 0;
+  std::mutex stage_mu;
   double *rf_d = nullptr, *out10_d = nullptr;
 
   cudaStream_t side = nullptr;
@@ -755,6 +757,19 @@ int run_core(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits, bool wit
   return 0;
 }
 
+int grow_frame_stage(uvlt_engine* e, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(e->stage_mu);  // uvlt_upload_frames may be called from several host threads
+  if (bytes <= e->frame_stage_bytes) return 0;
+  // first frame of a sequence (or a larger video): grow the staging buffer
+  ENG_CUDA(cudaStreamSynchronize(s));
+  if (e->frame_stage) cudaFree(e->frame_stage);
+  e->frame_stage = nullptr;
+  e->frame_stage_bytes = 0;
+  ENG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->frame_stage), bytes));
+  e->frame_stage_bytes = bytes;
+  return 0;
+}
+
 int check_text_cache(uvlt_engine* e, int B, bool cached, bool logits) {
   if (!cached) return 0;
   if (logits) { set_error("UVLT_TEXT_CACHED cannot be combined with UVLT_WANT_LOGITS (per-layer text tokens are needed)"); return 1; }
@@ -1064,7 +1079,7 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
                                 double* out_host, void* stream) {
   if (!e) { set_error("null handle"); return 1; }
   if (check_batch(e, B)) return 1;
-  if (!frames_host || !state || !tmpl || !ids || !text_mask || !prompt || !flag || !window || !out_host) {
+  if (!state || !tmpl || !ids || !text_mask || !prompt || !flag || !window || !out_host) {
     set_error("uvlt_track_frame_image_host: null argument");
     return 1;
   }
@@ -1080,15 +1095,13 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
   if (!p) return 1;
   e->launch_count = 0;
   const size_t bytes = static_cast<size_t>(B) * frame_h * frame_w * 3;
-  if (bytes > e->frame_stage_bytes) {  // first frame of a sequence (or a larger video): grow the staging buffer
-    ENG_CUDA(cudaStreamSynchronize(s));
-    if (e->frame_stage) cudaFree(e->frame_stage);
-    e->frame_stage = nullptr;
-    e->frame_stage_bytes = 0;
-    ENG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->frame_stage), bytes));
-    e->frame_stage_bytes = bytes;
+  if (frames_host) {
+    if (grow_frame_stage(e, bytes, s)) return 1;
+    ENG_CUDA(cudaMemcpyAsync(e->frame_stage, frames_host, bytes, cudaMemcpyHostToDevice, s));
+  } else if (bytes > e->frame_stage_bytes) {  // frames_host == NULL: the frames were sent with uvlt_upload_frames
+    set_error("uvlt_track_frame_image_host: no frames uploaded for this batch / frame size");
+    return 1;
   }
-  ENG_CUDA(cudaMemcpyAsync(e->frame_stage, frames_host, bytes, cudaMemcpyHostToDevice, s));
   CropParams cp{e->frame_stage, frame_h, frame_w, state, search_factor, e->Hx, e->u8_stage, e->rf_d};
   UVLT_LAUNCH(crop_resize_kernel, dim3((e->Hx * e->Hx + 255) / 256, B), dim3(256), 0, s, cp);
   if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
@@ -1115,6 +1128,16 @@ int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w,
   UVLT_LAUNCH(crop_resize_kernel, dim3((out_size * out_size + 255) / 256, B), dim3(256), 0,
               static_cast<cudaStream_t>(stream), cp);
   if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
+  return 0;
+}
+
+int uvlt_upload_frames(uvlt_handle e, const uint8_t* host, int64_t dst_offset, int64_t nbytes, int64_t total_bytes,
+                       void* stream) {
+  if (!e || !host) { set_error("uvlt_upload_frames: null argument"); return 1; }
+  if (dst_offset < 0 || nbytes < 0 || dst_offset + nbytes > total_bytes) { set_error("uvlt_upload_frames: bad range"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s)) return 1;
+  ENG_CUDA(cudaMemcpyAsync(e->frame_stage + dst_offset, host, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, s));
   return 0;
 }
 

@@ -257,15 +257,22 @@ class Engine:
 
     def track_frame_image_host(self, frames_pinned, state_dev, search_factor, template, ids, text_mask, prompt, flag,
                                window, out_pinned, batch, has_cont=True, skip_text=False, max_score=None, snapshot=None,
-                               text_cached=False):
+                               text_cached=False, uploaded=False):
         """One tracker step from the raw frames (pinned uint8 [B,H,W,3]): crop + resize, forward, merge and box update
         all on the device; ``state_dev`` (fp64 [B,4]) is updated in place, ``out_pinned`` (fp64 [B,10]) receives the rows.
         Synchronises the stream."""
         B, H, W, _ = frames_pinned.shape
         _cabi.check(self.lib.uvlt_track_frame_image_host(
-            self.h, C.c_void_p(frames_pinned.data_ptr()), int(H), int(W), _cabi.ptr(state_dev), float(search_factor),
+            self.h, None if uploaded else C.c_void_p(frames_pinned.data_ptr()), int(H), int(W), _cabi.ptr(state_dev),
+            float(search_factor),
             _cabi.ptr(template), _cabi.ptr(ids), _cabi.ptr(text_mask), _cabi.ptr(prompt), _cabi.ptr(flag),
             _cabi.ptr(window), int(batch), (_cabi.SKIP_TEXT if skip_text else 0) | (_cabi.TEXT_CACHED if text_cached else 0),
             int(has_cont), _cabi.ptr(max_score), _cabi.ptr(snapshot), C.c_void_p(out_pinned.data_ptr()),
             _cabi.current_stream()), "uvlt_track_frame_image_host")
         return out_pinned
+
+    def upload_frames(self, pinned_piece, dst_offset: int, total_bytes: int):
+        """Enqueue the H2D copy of one piece of the next step's frames (see uvlt_upload_frames)."""
+        _cabi.check(self.lib.uvlt_upload_frames(self.h, C.c_void_p(pinned_piece.data_ptr()), int(dst_offset),
+                                                int(pinned_piece.numel() * pinned_piece.element_size()), int(total_bytes),
+                                                _cabi.current_stream()), "uvlt_upload_frames")

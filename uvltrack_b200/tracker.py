@@ -145,6 +145,8 @@ class BatchTracker:
         self.out10 = torch.zeros(self.B, 10, dtype=torch.float64, pin_memory=True)
         self.out10_np = self.out10.numpy()
         self.frames = None  # pinned uint8 [B, H, W, 3], allocated for the first frame size seen
+        self._fast = None   # raw pointers of the per-frame engine call, bound per frame size
+        self._pool = None
         self.skip_text = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -234,6 +236,17 @@ class BatchTracker:
         self.frame_id = 0
         torch.cuda.synchronize()
 
+    def _bind_fast_path(self, H, W):
+        """Raw device / pinned pointers of everything the per-frame call takes (the tensors are allocated once in
+        __init__ and never reallocated), so that track() does no tensor slicing or pointer marshalling per frame."""
+        self._fast = {
+            "hw": (H, W), "frames_ptr": self.frames.data_ptr(), "total": self.frames.numel(),
+            "state": self.state_dev.data_ptr(), "template": self.template.data_ptr(), "ids": self.ids.data_ptr(),
+            "text_mask": self.text_mask.data_ptr(), "prompt": self.prompt.data_ptr(), "flag": self.flag.data_ptr(),
+            "window": self.window_dev.data_ptr(), "max_score": self.max_score_dev.data_ptr(),
+            "snapshot": self.snapshot.data_ptr(), "out10": self.out10.data_ptr(),
+        }
+
     def track(self, images):
         """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch."""
         import torch
@@ -251,13 +264,40 @@ class BatchTracker:
             if self.frames is None or tuple(self.frames.shape[1:3]) != (H, W):
                 self.frames = torch.empty(self.B, H, W, 3, dtype=torch.uint8, pin_memory=True)
                 self.frames_np = self.frames.numpy()
-            for b, image in enumerate(images):
-                np.copyto(self.frames_np[b], image)
-            self.engine.track_frame_image_host(self.frames, self.state_dev, self.params.search_factor, self.template,
-                                               self.ids, self.text_mask, self.prompt, self.flag, self.window_dev,
-                                               self.out10, self.B, has_cont=self.has_cont, skip_text=self.skip_text,
-                                               max_score=self.max_score_dev, snapshot=self.snapshot,
-                                               text_cached=self.text_cached)
+                self._fast = None
+            # pageable frame -> pinned staging -> H2D, one piece per sequence so that the DMA of one piece overlaps the
+            # host copy of the next; with several sequences the host copies run on a small thread pool (numpy and the
+            # C call release the GIL).  All arguments of the engine call are raw pointers bound once per frame size.
+            if self._fast is None or self._fast["hw"] != (H, W):
+                self._bind_fast_path(H, W)
+            f = self._fast
+            stream = torch.cuda.current_stream().cuda_stream
+            lib, h = self.engine.lib, self.engine.h
+            per = H * W * 3
+
+            def stage(b):
+                np.copyto(self.frames_np[b], images[b])
+                if lib.uvlt_upload_frames(h, f["frames_ptr"] + b * per, b * per, per, f["total"], stream):
+                    raise RuntimeError("uvlt_upload_frames failed")
+
+            if self.B == 1:
+                stage(0)
+            else:
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+
+                    dev = torch.cuda.current_device()
+                    self._pool = ThreadPoolExecutor(max_workers=min(8, self.B),
+                                                    initializer=lambda: torch.cuda.set_device(dev))
+                list(self._pool.map(stage, range(self.B)))
+            rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
+                                                 f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
+                                                 (2 if self.skip_text else 0) | (4 if self.text_cached else 0),
+                                                 int(self.has_cont), f["max_score"], f["snapshot"], f["out10"], stream)
+            if rc:
+                from . import _cabi
+
+                _cabi.check(rc, "uvlt_track_frame_image_host")
             rows = []
             for b in range(self.B):
                 row = self.out10_np[b]
