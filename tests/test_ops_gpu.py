@@ -19,6 +19,9 @@ def rel(a, b):
     (513, 3072, 768, 0, 1, False, False), (513, 768, 3072, 0, 0, True, True), (40, 768, 768, 0, 0, True, True),
     (1, 768, 768, 0, 0, False, True), (129, 96, 64, 32, 2, False, False), (17696, 2304, 768, 128, 0, False, False),
     (256, 1024, 6912, 0, 2, False, False),
+    # 128 x 256 tiles (large-M throughput configuration): every epilogue flavour, M tail, two-pass fp32 epilogue
+    (1300, 2304, 768, 256, 0, False, False), (1300, 3072, 768, 256, 1, False, False), (1300, 768, 3072, 256, 0, True, True),
+    (200, 1024, 128, 256, 2, False, False),
 ])
 def test_gemm(M, N, K, bn, act, resid, f32):
     lib = _cabi.load()

@@ -939,7 +939,7 @@ int uvlt_set_option(uvlt_handle e, const char* name, int32_t value) {
       for (auto& g : kv.second->graph)
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   } else if (n == "bn") {
-    if (value != 0 && value != 32 && value != 64 && value != 128) { set_error("bn must be 0/32/64/128"); return 1; }
+    if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) { set_error("bn must be 0/32/64/128/256"); return 1; }
     e->force_bn = value;
     cudaDeviceSynchronize();
     for (auto& kv : e->plans)

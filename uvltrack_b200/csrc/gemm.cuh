@@ -58,7 +58,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;   // 2 * GEMM_MAX_STAGES + 1 mbarriers + the TMEM slot
   static constexpr int BIAS_BYTES = BN * 4;
-  static constexpr int EPI_BYTES = GEMM_BM * BN * 4;  // fp32 staging tile of the epilogue, aliases the operand ring
+  // staging tile of the epilogue (aliases the operand ring): fp32 flavour in passes of <= 128 columns, bf16 whole tile
+  static constexpr int EPI_BYTES = GEMM_BM * (BN > 128 ? 128 : BN) * 4;
   // dynamic smem for a ring of `stages`: [ring, 1024-aligned][barriers][bias]
   static constexpr int total(int stages) {
     return (stages * STAGE_BYTES > EPI_BYTES ? stages * STAGE_BYTES : EPI_BYTES) + BAR_BYTES + BIAS_BYTES;
@@ -138,8 +139,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN)
-    s_bias[threadIdx.x - 64] = (ep.bias && sp == 0) ? __ldg(ep.bias + g * ep.bias_gstride + n0 + (threadIdx.x - 64)) : 0.0f;
+  if (threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += GEMM_THREADS - 64)
+      s_bias[i] = (ep.bias && sp == 0) ? __ldg(ep.bias + g * ep.bias_gstride + n0 + i) : 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   if (MC) cluster_sync_all();  // the peer's barriers must be initialised before our multicast can signal them
@@ -214,27 +217,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int lane_grp = warp & 3;  // TMEM lane quadrant this warp may access
     constexpr bool F32 = (EPI == EPI_F32);
     constexpr int ESZ = F32 ? 4 : 2;            // staged element size: the bf16 flavours convert in stage 1
-    constexpr int ROWB = BN * ESZ;              // bytes per staged row
+    constexpr int PW = (F32 && BN > 128) ? 128 : BN;  // columns per epilogue pass (the staging tile is <= 64 KB)
+    constexpr int NPASS = BN / PW;
+    constexpr int ROWB = PW * ESZ;              // bytes per staged row
     constexpr int CPR = ROWB / 16;              // 16-byte chunks per staged row
     constexpr int RPI = 32 / CPR;               // rows covered by one warp instruction in stage 2
     constexpr int ITERS = 32 / RPI;
     constexpr int SWZ = (CPR < 8 ? CPR : 8) - 1;  // XOR swizzle of the chunk index with the row, kept inside the row
     const uint32_t stage_w = smem_u32(smem) + lane_grp * 32 * ROWB;  // this warp's 32 rows of the staging tile
     const int j2 = lane % CPR;
-    const int col = n0 + j2 * (16 / ESZ);
+    const int col0 = n0 + j2 * (16 / ESZ);
     const int r_first = m0 + lane_grp * 32 + lane / CPR;  // this lane's rows are r_first + it * RPI
     // position of the first row inside its sequence / inside the periodic residual table, computed while the mainloop
     // runs; advanced incrementally afterwards (the periods are >= 8 rows on this path, checked on the host)
-    int seq_q = 0, seq_rem = r_first, per_rem = 0;
+    int seq_q0 = 0, seq_rem0 = r_first, per_rem0 = 0;
     if (F32) {
-      if (ep.in_rows_per_b > 0) { seq_q = r_first / ep.in_rows_per_b; seq_rem = r_first - seq_q * ep.in_rows_per_b; }
-      if (ep.resid_period > 0) per_rem = r_first % ep.resid_period;
+      if (ep.in_rows_per_b > 0) { seq_q0 = r_first / ep.in_rows_per_b; seq_rem0 = r_first - seq_q0 * ep.in_rows_per_b; }
+      if (ep.resid_period > 0) per_rem0 = r_first % ep.resid_period;
     }
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TRACE_PT(0x105);
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; ++pass) {
+    const int col = col0 + pass * PW;
+    int seq_q = seq_q0, seq_rem = seq_rem0, per_rem = per_rem0;
     {
-      const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16);
+      const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + pass * PW;
       const uint32_t my_row = stage_w + lane * ROWB;
       uint32_t va[32], vb[32];
       // 32 accumulator columns: + bias (+ activation, -> bf16) -> swizzled staging row
@@ -242,7 +251,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         if (F32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 4);
             const int j = ((c >> 2) + q) ^ (lane & SWZ);
             sts128(my_row + j * 16, __uint_as_float(v[q * 4]) + b4.x, __uint_as_float(v[q * 4 + 1]) + b4.y,
                    __uint_as_float(v[q * 4 + 2]) + b4.z, __uint_as_float(v[q * 4 + 3]) + b4.w);
@@ -250,8 +259,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float4 x0 = *reinterpret_cast<const float4*>(s_bias + c + q * 8);
-            float4 x1 = *reinterpret_cast<const float4*>(s_bias + c + q * 8 + 4);
+            float4 x0 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8);
+            float4 x1 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8 + 4);
             x0.x += __uint_as_float(v[q * 8]);     x0.y += __uint_as_float(v[q * 8 + 1]);
             x0.z += __uint_as_float(v[q * 8 + 2]); x0.w += __uint_as_float(v[q * 8 + 3]);
             x1.x += __uint_as_float(v[q * 8 + 4]); x1.y += __uint_as_float(v[q * 8 + 5]);
@@ -270,14 +279,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tmem_ld32(t_row, va);
       tmem_wait_ld_dep(va);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {
-        if (c + 32 < BN) tmem_ld32(t_row + c + 32, vb);
+      for (int c = 0; c < PW; c += 64) {
+        if (c + 32 < PW) tmem_ld32(t_row + c + 32, vb);
         stage1(va, c);
-        if (c + 32 < BN) {
+        if (c + 32 < PW) {
           tmem_wait_ld_dep(vb);
-          if (c + 64 < BN) tmem_ld32(t_row + c + 64, va);
+          if (c + 64 < PW) tmem_ld32(t_row + c + 64, va);
           stage1(vb, c + 32);
-          if (c + 64 < BN) tmem_wait_ld_dep(va);
+          if (c + 64 < PW) tmem_wait_ld_dep(va);
         }
       }
     }
@@ -335,6 +344,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
       }
     }
+    __syncwarp();  // stage 2 has read this pass before the next pass overwrites the staging rows
+    }  // pass
     if (threadIdx.x == 64) TRACE_PT(0x106);
   }
 

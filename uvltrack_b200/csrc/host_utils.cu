@@ -66,6 +66,7 @@ int init_kernel_attributes() {
   UVLT_GEMM_ATTR_BN(32);
   UVLT_GEMM_ATTR_BN(64);
   UVLT_GEMM_ATTR_BN(128);
+  UVLT_GEMM_ATTR_BN(256);
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
@@ -81,7 +82,12 @@ int g_gemm_multicast = [] {
   return (e && e[0] == '1') ? 1 : 0;
 }();
 
-int pick_bn(int M, int N, int groups) {
+int pick_bn(int M, int N, int groups, bool out_f32) {
+  // 128 x 256 tiles halve the A-operand smem reads per FLOP and cut the L2 -> SM operand traffic by a quarter: measured
+  // 862 -> 1029 TFLOP/s on the qkv GEMM at M = 16416, but slower for the fp32-output GEMMs (N = 768: only three N tiles,
+  // two-pass epilogue) and whenever the grid is below ~2.5 waves of 2 x 148 CTAs (profiles/r01_gemm_bn256.txt)
+  if (!out_f32 && N % 256 == 0 && static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / 256) * groups >= 740)
+    return 256;
   // Widest tile that still gives one CTA per SM (148) (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
   // which bounds these launches, until fewer than ~2/3 of the SMs have work); below that, the narrowest legal tile.
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
@@ -116,8 +122,8 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     }
     if (bn == 0) bn = 128;
   }
-  if (bn == 0) bn = pick_bn(M, N, groups);
-  if (bn != 32 && bn != 64 && bn != 128) {
+  if (bn == 0) bn = pick_bn(M, N, groups, ep.out_f32 != 0);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
     set_error("gemm: N must be a multiple of 32");
     return 1;
   }
@@ -143,7 +149,8 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   g->shape = GemmShape{M, N, K, 0, splits};
   {
     // ring depth: ~100 KB so that two CTAs share an SM (epilogue / mainloop overlap, and PDL residency of the next kernel)
-    const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA : GemmSmem<128>::STAGES_2CTA;
+    const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA
+                   : bn == 128 ? GemmSmem<128>::STAGES_2CTA : GemmSmem<256>::STAGES_2CTA;
     g->shape.stages = std::max(std::min(s2, K / GEMM_BK / splits), 1);
   }
   g->ep = ep;
@@ -181,12 +188,14 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
     switch (g.bn) {
       case 32: gemm_launch_bn<32, true>(g, grid, stream); break;
       case 64: gemm_launch_bn<64, true>(g, grid, stream); break;
+      case 256: gemm_launch_bn<256, true>(g, grid, stream); break;
       default: gemm_launch_bn<128, true>(g, grid, stream); break;
     }
   } else {
     switch (g.bn) {
       case 32: gemm_launch_bn<32, false>(g, grid, stream); break;
       case 64: gemm_launch_bn<64, false>(g, grid, stream); break;
+      case 256: gemm_launch_bn<256, false>(g, grid, stream); break;
       default: gemm_launch_bn<128, false>(g, grid, stream); break;
     }
   }
