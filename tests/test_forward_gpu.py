@@ -18,7 +18,8 @@ from uvltrack_b200.weights import synthetic_inputs, synthetic_state_dict
 pytestmark = pytest.mark.gpu
 
 PX = 1.0 / 256.0  # one pixel of the 256^2 search crop in normalised coordinates
-CLS_MAX_ABS = 3e-2
+CLS_MAX_ABS = 3e-2        # sharpened synthetic cls tower (x4 on top of x2 conv gains), 12-layer model
+CLS_MAX_ABS_LARGE = 4e-2  # 24 layers accumulate ~sqrt(2) more bf16 rounding noise in the features
 
 
 def T(a):
@@ -39,9 +40,10 @@ def case(request):
     model.engine.close()
 
 
-def _check_head(out, g, prefix=""):
+def _check_head(out, g, prefix="", large=False):
     assert rel_l2(out["cls_score_test"].cpu().numpy(), g[prefix + ("cls" if prefix else "cls_score_test")]) < BF16_REL_L2
-    assert max_abs(out["cls_score_test"].cpu().numpy(), g[prefix + ("cls" if prefix else "cls_score_test")]) < CLS_MAX_ABS
+    assert max_abs(out["cls_score_test"].cpu().numpy(), g[prefix + ("cls" if prefix else "cls_score_test")]) < \
+        (CLS_MAX_ABS_LARGE if large else CLS_MAX_ABS)
     for k in ("bbox_map", "cont_score"):
         assert rel_l2(out[k].cpu().numpy(), g[prefix + k]) < BF16_REL_L2, k
     assert max_abs(out["bbox_map"].cpu().numpy(), g[prefix + "bbox_map"]) < 2.56 * PX
@@ -53,7 +55,7 @@ def test_forward_test_matches_reference(case):
     out = model.forward_test(T(inp["template"]), T(inp["search"]), text, T(inp["prompt"]), T(inp["flag"]))
     torch.cuda.synchronize()
     assert model.engine.last_launch_count > 50  # the CUDA path ran (kernels counted by the library)
-    _check_head(out, g)
+    _check_head(out, g, large=meta["arch"] == "large")
     for k in ("logits", "vis_token", "txt_token"):
         assert rel_l2(out[k].cpu().numpy(), g[k]) < BF16_REL_L2, k
     assert rel_l2(out["search"].cpu().numpy()[:, ::8, ::4], g["search_sub"]) < BF16_REL_L2
@@ -116,7 +118,7 @@ def test_prompter_and_training_forward(case):
     assert rel_l2(prompt.cpu().numpy(), g["prompt_init"]) < BF16_REL_L2
     out = model.forward(T(inp["template"]), T(inp["search"]), text, tm, cm, T(inp["flag"]))
     assert out["cont_score"].shape[-1] == 2
-    _check_head(out, g, prefix="train_")
+    _check_head(out, g, prefix="train_", large=meta["arch"] == "large")
     # forward_prompt on the dict returned by forward_test == forward_prompt_init on the same inputs
     o2 = model.forward_test(T(inp["template"]), T(inp["search"]), text, T(inp["prompt"]), T(inp["flag"]))
     p2 = model.forward_prompt(o2, tm, cm)

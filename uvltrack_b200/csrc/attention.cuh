@@ -5,33 +5,31 @@
 // dialects are an additive per-key fp32 bias here (adding -1e10 to an O(10) fp32 score is exactly -1e10).
 //
 // QKV layout in HBM: bf16 [B, n, 3*H*64] exactly as the qkv GEMM writes it (token-major, [which][head][64]).
-// One CTA = one (batch, head, 128-query tile).  192 threads:
-//   warp 0      TMA producer : Q tile once, then K_j / V_j tiles (128 keys x 64) through a 2-stage ring
-//   warp 1      MMA issuer   : S_j = Q K_j^T   (tcgen05, M=128, N<=128, K=64)  -> TMEM cols [0,128)
-//                              O  += P_j V_j   (tcgen05, M=128, N=64,  K<=128) -> TMEM cols [128,192)
-//                              V is consumed straight from its [key][64] tile as an MN-major B operand.
-//   warps 2..5  softmax      : thread = query row; online softmax in the exp2 domain with fp32 statistics.  TMEM reads
-//                              run at 64 B/cycle/SM, so an unmasked full block reads S ONCE (tcgen05.ld, software
-//                              pipelined 32 columns at a time): P = 2^(s*scale - ref) against the running reference
-//                              (one FFMA + one MUFU.EX2 + one FADD per score), the block maximum is tracked on the side
-//                              with 3-input max and only moves the reference of LATER blocks, and only when it grew by
-//                              more than 2^8; O / l are rescaled in TMEM when (rarely) the reference moves.  The exact
-//                              result is unchanged: P, l and O share the reference and O / l cancels it.  Masked or
-//                              partial blocks take a two-pass path with per-key bias.  P_j -> bf16 -> swizzled smem
-//                              (A operand of the PV MMA).
-// 112.25 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM: one CTA's softmax (MUFU bound: 16384
-// exp2 per 128x128 tile = 1024 cycles per SM) overlaps the other's MMAs (512 tensor cycles per tile at head dim 64).
+// One CTA = one (batch, head, 128-query tile), 64 keys per block, 192 threads:
+//   warp 0      TMA producer : Q tile once, then K_j / V_j tiles (64 keys x 64) through a 2-stage ring
+//   warp 1      MMA issuer   : S_j = Q K_j^T (tcgen05 M=128, N<=64, K=64) -> TMEM cols [0,64); O += P_j V_j (M=128, N=64,
+//                              K<=64) -> TMEM cols [64,128).  V is consumed straight from its [key][64] tile as an MN-major
+//                              B operand.  All descriptors are built before the loop.
+//   warps 2..5  softmax      : thread = query row.  One wide tcgen05.ld brings the 64 scores of the block into registers
+//                              and S is released at once (QK_{j+1} overlaps the softmax of block j); row maximum (3-input
+//                              max), exp2 against the running reference (FFMA + ex2.approx + FADD per score; the reference
+//                              moves only when the maximum grew by > 2^8, then O / l are rescaled in TMEM), P -> bf16 ->
+//                              swizzled smem (A operand of the PV MMA).  Masked / partial blocks use the same registers
+//                              with the additive per-key bias.
+// The per-block chain of a CTA is latency bound (every barrier wait / arrive / fence costs a lone warp 100-250 cycles of
+// issue stall, profiles/r01_attention_experiments.md), so the kernel is built for residency instead: 64.3 KB of shared
+// memory, 128 TMEM columns and <= 112 registers per thread -> THREE CTAs per SM whose chains interleave.
 #pragma once
 #include "common.cuh"
 
 namespace uvlt {
 
 constexpr int ATT_BQ = 128;    // queries per CTA
-constexpr int ATT_BKV = 128;   // keys per block
+constexpr int ATT_BKV = 64;    // keys per block
 constexpr int ATT_D = 64;      // head dim (both UVLTrack-B and -L)
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_STAGES = 2;
-constexpr int ATT_MAX_KV = 4096;  // 32 key blocks (bit mask of biased blocks)
+constexpr int ATT_MAX_KV = 2048;  // 32 key blocks (bit mask of biased blocks)
 
 struct AttnParams {
   int n;               // sequence length (queries == keys)
@@ -43,14 +41,14 @@ struct AttnParams {
 
 struct AttnSmem {
   static constexpr int Q_BYTES = ATT_BQ * ATT_D * 2;       // 16 KB
-  static constexpr int KV_BYTES = ATT_BKV * ATT_D * 2;     // 16 KB each
-  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;     // 32 KB (two 64-wide K halves)
+  static constexpr int KV_BYTES = ATT_BKV * ATT_D * 2;     // 8 KB each
+  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;     // 16 KB per buffer
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + ATT_STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + ATT_STAGES * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 256;  // 114944 B: 2 x (TOTAL + 1 KB reserved) <= 228 KB per SM
+  static constexpr int TOTAL = OFF_BAR + 256;  // 65792 B: 3 x (TOTAL + 1 KB reserved) <= 228 KB per SM
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -131,8 +129,8 @@ __device__ __forceinline__ float chunk_exp_dyn(int mode, const uint32_t (&v)[32]
   return chunk_exp<2>(v, pk, scale, neg_m, bias_c, lim);
 }
 
-static __global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+static __global__ void __launch_bounds__(ATT_THREADS, 3)
+attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t att_smem[];  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
   uint8_t* const smem = att_smem;
   uint8_t* sQ = smem + AttnSmem::OFF_Q;
@@ -141,12 +139,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   uint8_t* sP = smem + AttnSmem::OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]
-  uint64_t* kv_empty = kv_full + ATT_STAGES;     // [ATT_STAGES]
+  uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]  K_j and V_j landed
+  uint64_t* kv_empty = kv_full + ATT_STAGES;     // [ATT_STAGES]  PV_j drained (K_j was consumed earlier by QK_j)
   uint64_t* s_full = kv_empty + ATT_STAGES;      // S_j landed in TMEM
-  uint64_t* s_empty = s_full + 1;                // softmax finished reading S_j (128 arrivals)
-  uint64_t* p_full = s_empty + 1;                // P_j in smem + O rescaled (128 arrivals)
-  uint64_t* pv_done = p_full + 1;                // PV_j drained: P buffer reusable, O consistent
+  uint64_t* s_empty = s_full + 1;                // the softmax warps hold S_j in registers (128 arrivals)
+  uint64_t* p_full = s_empty + 1;                // P_j in smem, O rescaled (128 arrivals)
+  uint64_t* pv_done = p_full + 1;                // PV_j drained: P buffer reusable, O includes block j
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -158,11 +156,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   const int nblk = (p.n + ATT_BKV - 1) / ATT_BKV;
 
   if (warp == 0 && lane == 0) {
-    if (smem_u32(smem) & 1023u) {
-      printf("uvlt: attention dynamic shared memory is not 1024-byte aligned\n");
-      __trap();
-    }
-    tma_prefetch_desc(&tma_qkv);
+    if (smem_u32(smem) & 1023u) __trap();  // dynamic shared memory must be 1024-byte aligned
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -175,15 +171,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + ATT_BKV;
+  const uint32_t tmem_S = tmem_base;             // 64 columns
+  const uint32_t tmem_O = tmem_base + ATT_BKV;   // 64 columns
   pdl_wait();  // bias and qkv come from earlier kernels of the chain
   pdl_trigger();
 
@@ -191,59 +187,68 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       mbar_expect_tx(q_full, AttnSmem::Q_BYTES);
-      tma_load_3d(sQ, &tma_qkv, q_full, h * ATT_D, q0, b);
+      tma_load_3d(sQ, &tma_q, q_full, h * ATT_D, q0, b);
+      int s = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % ATT_STAGES;
-        const uint32_t ph = (j / ATT_STAGES) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * AttnSmem::KV_BYTES);
-        tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_qkv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
-        tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_qkv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
+        tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
+        tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
+        if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
+      const int last_valid = p.n - (nblk - 1) * ATT_BKV;  // keys in the last block
+      const uint32_t idesc_full = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0);
+      const uint32_t idesc_last = umma_idesc_bf16(ATT_BQ, (last_valid + 15) & ~15, 0);  // UMMA N granularity 16
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 1);
+      const uint64_t qd = umma_smem_desc_sw128(smem_u32(sQ), 1024, 0);
+      const uint64_t kd_base = umma_smem_desc_sw128(smem_u32(sK), 1024, 0);       // + stage * (KV_BYTES >> 4)
+      // V: [key][64] rows of 128 B = MN-major B operand; 16 keys = 16 rows = 2048 B (+128 in the 16-byte address field)
+      const uint64_t vd_base = umma_smem_desc_sw128(smem_u32(sV), 1024, 1024);
+      // P: [128 x 64] K-major; 16 keys = 32 B inside the swizzle atom (+2 in the address field)
+      const uint64_t pd_base = umma_smem_desc_sw128(smem_u32(sP), 1024, 0);       // + buffer * (P_BYTES >> 4)
+      constexpr uint64_t KV_STEP = AttnSmem::KV_BYTES >> 4;
+      int sq = 0;            // ring stage of the next QK
+      uint32_t phq = 0;      // its kv_full parity
       auto issue_qk = [&](int j) {
-        const int s = j % ATT_STAGES;
-        const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
-        const int ncols = (kv_valid + 15) & ~15;  // UMMA N granularity at M=128
-        const uint32_t idesc = umma_idesc_bf16(ATT_BQ, ncols, 0);
-        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sQ), 1024, 0);
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sK + s * AttnSmem::KV_BYTES), 1024, 0);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem_S, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+        const uint64_t kd = kd_base + KV_STEP * sq;
+        const uint32_t idesc = (j == nblk - 1) ? idesc_last : idesc_full;
+        umma_bf16_ss(tmem_S, qd, kd, idesc, 0u);
+        umma_bf16_ss(tmem_S, qd + 2, kd + 2, idesc, 1u);
+        umma_bf16_ss(tmem_S, qd + 4, kd + 4, idesc, 1u);
+        umma_bf16_ss(tmem_S, qd + 6, kd + 6, idesc, 1u);
         umma_commit(s_full);
+        if (++sq == ATT_STAGES) { sq = 0; phq ^= 1; }
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_qk(0);
+      int sv = 0;  // ring stage of the next PV
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % ATT_STAGES;
         if (j + 1 < nblk) {
-          // S_j has been consumed by the softmax warps -> overwrite with S_{j+1} while they finish P_j
+          // the softmax warps hold S_j in registers -> overwrite it with S_{j+1} while they compute P_j
+          mbar_wait(&kv_full[sq], phq);
           mbar_wait(s_empty, j & 1);
-          mbar_wait(&kv_full[(j + 1) % ATT_STAGES], ((j + 1) / ATT_STAGES) & 1);
           tc_fence_after();
           issue_qk(j + 1);
         }
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
-        const int ksteps = (kv_valid + 15) >> 4;
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_D, 1);
-        const uint32_t p_addr = smem_u32(sP);
-        const uint32_t v_addr = smem_u32(sV + s * AttnSmem::KV_BYTES);
-        for (int k = 0; k < ksteps; ++k) {
-          // P: two [128 x 64] K-major halves; 16 keys = 32 B inside the swizzle atom
-          const uint64_t adesc = umma_smem_desc_sw128(p_addr + (k >> 2) * (AttnSmem::P_BYTES / 2), 1024, 0) + 2 * (k & 3);
-          // V: [key][64] rows of 128 B = MN-major B operand; 16 keys = 16 rows = 2048 B
-          const uint64_t bdesc = umma_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
-          umma_bf16_ss(tmem_O, adesc, bdesc, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&kv_empty[s]);
+        const int ksteps = (j == nblk - 1) ? ((last_valid + 15) >> 4) : (ATT_BKV / 16);
+        const uint64_t vd = vd_base + KV_STEP * sv;
+        const uint64_t pd = pd_base;
+        umma_bf16_ss(tmem_O, pd, vd, idesc_pv, j > 0 ? 1u : 0u);
+        if (ksteps > 1) umma_bf16_ss(tmem_O, pd + 2, vd + 128, idesc_pv, 1u);
+        if (ksteps > 2) umma_bf16_ss(tmem_O, pd + 4, vd + 256, idesc_pv, 1u);
+        if (ksteps > 3) umma_bf16_ss(tmem_O, pd + 6, vd + 384, idesc_pv, 1u);
+        umma_commit(&kv_empty[sv]);
         umma_commit(pv_done);
+        if (++sv == ATT_STAGES) sv = 0;
       }
     }
   } else {
@@ -265,107 +270,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         if (__any_sync(0xffffffffu, nz)) biased |= 1u << j;
       }
     }
-    float m_run = -INFINITY;  // reference wanted for the next block (scaled log2 domain): the largest score seen,
-                              // updated only when it grows by more than 2^8
-    float o_ref = -INFINITY;  // reference the TMEM output and l_run are currently expressed in
+    float m_run = -INFINITY;  // reference of the running sum / output (scaled log2 domain): the largest score seen,
+                              // moved only when the maximum grows by more than 2^8 (P stays <= 256; exact after O / l)
     float l_run = 0.0f;
-    uint8_t* const p_row = sP + row * 128;
-    auto store_p = [&](int c, const uint32_t (&pk)[16]) {
-      // 32 keys = four 16 B chunks of this row; chunk index inside the 64-key half is XOR-swizzled with row%8
-      uint8_t* half_base = p_row + (c >> 1) * (AttnSmem::P_BYTES / 2);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-        *reinterpret_cast<uint4*>(half_base + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-      }
-    };
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
-      const int nchunk = (kv_valid + 31) >> 5;
+      const int nchunk = (((kv_valid + 15) & ~15) + 31) >> 5;  // 32-key chunks the PV MMA may read: must be written
       const int mode = ((biased >> j) & 1u) ? 2 : (kv_valid < ATT_BKV ? 1 : 0);  // block-uniform
       const float* bj = p.bias ? p.bias + static_cast<long long>(b) * p.n + j * ATT_BKV : nullptr;
+      uint32_t v[2][32], pk[16];
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-
-      float ref;            // exp reference of this block's P (per row)
-      float m_blk;          // this block's row maximum
-      float l_blk = 0.0f;
-      bool two_pass = mode != 0;
-      uint32_t va[32], vb[32], pk[16];
-      if (!two_pass) {
-        // ---- single pass (TMEM reads are 64 B/cycle/SM: S is read once).  Reference = the running one; on the first
-        //      block the maximum of the first 32 keys.  P may exceed 1 by up to the growth of the maximum, which bf16 /
-        //      fp32 represent exactly as well; beyond 2^64 the block is redone with its own maximum. ----
-        tmem_ld32(tmem_S + lane_off, va);
-        tmem_wait_ld_dep(va);
-        const float c0 = chunk_max<0>(va, scale, nullptr, 32);
-        ref = (m_run == -INFINITY) ? c0 : m_run;
-        const float neg_ref = -ref;
-        float mx = c0;
-        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P buffer free once PV_{j-1} has drained
-        tmem_ld32(tmem_S + lane_off + 32, vb);
-        l_blk += chunk_exp<0>(va, pk, scale, neg_ref, nullptr, 32);
-        store_p(0, pk);
-        tmem_wait_ld_dep(vb);
-        tmem_ld32(tmem_S + lane_off + 64, va);
-        mx = fmaxf(mx, chunk_max<0>(vb, scale, nullptr, 32));
-        l_blk += chunk_exp<0>(vb, pk, scale, neg_ref, nullptr, 32);
-        store_p(1, pk);
-        tmem_wait_ld_dep(va);
-        tmem_ld32(tmem_S + lane_off + 96, vb);
-        mx = fmaxf(mx, chunk_max<0>(va, scale, nullptr, 32));
-        l_blk += chunk_exp<0>(va, pk, scale, neg_ref, nullptr, 32);
-        store_p(2, pk);
-        tmem_wait_ld_dep(vb);
-        mx = fmaxf(mx, chunk_max<0>(vb, scale, nullptr, 32));
-        l_blk += chunk_exp<0>(vb, pk, scale, neg_ref, nullptr, 32);
-        store_p(3, pk);
-        m_blk = mx;
-        two_pass = __any_sync(0xffffffffu, m_blk > ref + 64.0f);  // overflow guard (never seen in practice)
-      }
-      if (two_pass) {
-        // ---- pass 1: block maximum (loads of chunk c+1 in flight while chunk c is reduced) ----
-        m_blk = -INFINITY;
-        tmem_ld32(tmem_S + lane_off, va);
-        tmem_wait_ld_dep(va);
-        for (int c = 0; c < nchunk; c += 2) {
-          if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
-          m_blk = fmaxf(m_blk, chunk_max_dyn(mode, va, scale, bj + c * 32, kv_valid - c * 32));
-          tmem_wait_ld_dep(vb);
-          if (c + 1 < nchunk) {
-            if (c + 2 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 2) * 32, va);
-            m_blk = fmaxf(m_blk, chunk_max_dyn(mode, vb, scale, bj + (c + 1) * 32, kv_valid - (c + 1) * 32));
-            tmem_wait_ld_dep(va);
-          }
-        }
-        // keep the stale reference unless the maximum grew by more than 2^8 (P stays <= 256, exact after O / l)
-        ref = (m_blk > m_run + 8.0f) ? m_blk : m_run;  // m_run = -inf on the first block -> m_blk
-        const float neg_ref = -ref;
-        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-        // ---- pass 2: probabilities -> bf16 -> swizzled smem, fp32 row sum ----
-        l_blk = 0.0f;
-        tmem_ld32(tmem_S + lane_off, va);
-        tmem_wait_ld_dep(va);
-        for (int c = 0; c < nchunk; c += 2) {
-          if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
-          l_blk += chunk_exp_dyn(mode, va, pk, scale, neg_ref, bj + c * 32, kv_valid - c * 32);
-          store_p(c, pk);
-          tmem_wait_ld_dep(vb);
-          if (c + 1 < nchunk) {
-            if (c + 2 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 2) * 32, va);
-            l_blk += chunk_exp_dyn(mode, vb, pk, scale, neg_ref, bj + (c + 1) * 32, kv_valid - (c + 1) * 32);
-            store_p(c + 1, pk);
-            tmem_wait_ld_dep(va);
-          }
-        }
-      }
-      // a partially filled 16-key MMA step may read up to the next 32-key boundary: covered (nchunk * 32 written)
+      // one wide TMEM load per block (every load -> wait round trip stalls the lone softmax warp of a scheduler for
+      // ~150-200 cycles; three narrow loads per block made the kernel 35 % slower)
+      tmem_ld64(tmem_S + lane_off, v[0], v[1]);
+      tmem_wait_ld_dep2(v[0], v[1]);
       tc_fence_before();
-      mbar_arrive(s_empty);
-      // bring the running output / sum to this block's reference (skipped warp-wide when no row moved)
+      mbar_arrive(s_empty);  // the scores are in registers: QK_{j+1} may overwrite S
+
+      // ---- block maximum and the exp reference ----
+      float m_blk;
+      if (mode == 0) {
+        m_blk = fmaxf(chunk_max<0>(v[0], scale, nullptr, 32), chunk_max<0>(v[1], scale, nullptr, 32));
+      } else {
+        m_blk = chunk_max_dyn(mode, v[0], scale, bj, kv_valid);
+        if (nchunk > 1) m_blk = fmaxf(m_blk, chunk_max_dyn(mode, v[1], scale, bj + 32, kv_valid - 32));
+      }
+      const float ref = (m_blk > m_run + 8.0f) ? m_blk : m_run;  // m_run = -inf on the first block -> m_blk
+      const float alpha = (ref == m_run) ? 1.0f : ex2_approx(m_run - ref);  // 0 on the first block
+      const float neg_ref = -ref;
+
+      // ---- the P buffer (and O) are free once PV_{j-1} has drained ----
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
       tc_fence_after();
-      const float alpha = (o_ref == ref) ? 1.0f : ex2_approx(o_ref - ref);  // 0 on the first block (o_ref = -inf)
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // bring the running output to the new reference (rare)
 #pragma unroll
         for (int c = 0; c < ATT_D; c += 32) {
           uint32_t o[32];
@@ -377,9 +315,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         }
         tmem_wait_st();
       }
+
+      // ---- probabilities -> bf16 -> swizzled smem ----
+      uint8_t* const p_row = sP + row * 128;
+      float l_blk = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < nchunk) {
+          if (mode == 0) l_blk += chunk_exp<0>(v[c], pk, scale, neg_ref, nullptr, 32);
+          else l_blk += chunk_exp_dyn(mode, v[c], pk, scale, neg_ref, bj + c * 32, kv_valid - c * 32);
+          // 32 keys = four 16 B chunks of this row; the chunk index is XOR-swizzled with row % 8 (128B swizzle)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c * 4 + q) ^ (row & 7);
+            *reinterpret_cast<uint4*>(p_row + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+      }
       l_run = l_run * alpha + l_blk;
-      o_ref = ref;
-      m_run = (m_blk > ref + 8.0f) ? m_blk : ref;
+      m_run = ref;
       fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
@@ -413,7 +367,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 

@@ -217,6 +217,7 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   const long long D3 = 3LL * H * ATT_D;
   // [B, n, 3D]: rows >= n are out of bounds inside each batch element -> TMA zero fill (no cross-sequence reads)
   if (make_tma_bf16_3d(&a->tma_qkv, qkv, D3, n, B, D3 * 2, static_cast<uint64_t>(n) * D3 * 2, ATT_BQ)) return 1;
+  if (make_tma_bf16_3d(&a->tma_kv, qkv, D3, n, B, D3 * 2, static_cast<uint64_t>(n) * D3 * 2, ATT_BKV)) return 1;
   a->p.n = n;
   a->p.H = H;
   a->p.scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim 64
@@ -228,7 +229,7 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
-  UVLT_LAUNCH(attention_kernel, grid, dim3(ATT_THREADS), AttnSmem::TOTAL, stream, a.tma_qkv, a.p);
+  UVLT_LAUNCH(attention_kernel, grid, dim3(ATT_THREADS), AttnSmem::TOTAL, stream, a.tma_qkv, a.tma_kv, a.p);
   UVLT_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -52,7 +52,8 @@ int pick_bn(int M, int N, int groups, bool out_f32);
 extern int g_gemm_multicast;  // UVLT_MULTICAST=0 disables the cluster / TMA-multicast GEMM variant
 
 struct AttnLaunch {
-  CUtensorMap tma_qkv;
+  CUtensorMap tma_qkv;  // 128-row boxes (Q tile)
+  CUtensorMap tma_kv;   // 64-row boxes (K / V tiles)
   AttnParams p;
   int B;
 };
