@@ -9,7 +9,8 @@
 //   warp 1      MMA issuer : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block, accumulator in TMEM
 //   warps 2..5  epilogue   : tcgen05.ld the fp32 accumulator (thread = row), bias / GELU / ReLU / residual,
 //                            vectorised global stores (bf16 or fp32)
-// Shared memory is sized so two CTAs are co-resident per SM: one CTA's epilogue overlaps the other's mainloop.
+// Shared memory is sized so two (latency regime) or three (throughput regime) CTAs are co-resident per SM: one CTA's
+// epilogue overlaps the others' mainloops.
 #pragma once
 #include "common.cuh"
 
@@ -64,10 +65,16 @@ struct GemmSmem {
   static constexpr int total(int stages) {
     return (stages * STAGE_BYTES > EPI_BYTES ? stages * STAGE_BYTES : EPI_BYTES) + BAR_BYTES + BIAS_BYTES;
   }
-  // ~100 KB of ring -> two CTAs per SM: one CTA's epilogue overlaps the other's mainloop, and under programmatic
-  // dependent launch the next kernel's CTAs become resident (and prefetch their weight tiles) while this one runs
-  static constexpr int STAGES_2CTA = (108 * 1024) / STAGE_BYTES > 8 ? 8 : (108 * 1024) / STAGE_BYTES;
-  static_assert(STAGES_2CTA * STAGE_BYTES >= EPI_BYTES, "epilogue staging must fit in the ring");
+  // Ring depth.  Latency regime (grid <= one wave of two CTAs per SM): ~100 KB, as much of K in flight as two
+  // co-resident CTAs allow, and under programmatic dependent launch the next kernel's CTAs become resident (and prefetch
+  // their weight tiles) while this one runs.  Throughput regime: ~70 KB so that THREE CTAs share an SM -- the epilogue
+  // of a tile is a latency chain of ~2.7k cycles on four lone warps, and a third CTA hides more of it
+  // (measured at M = 16416: proj 43.5 -> 36.4 us, fc1 116 -> 100.5 us, fc2 92.6 -> 87.4 us).
+  static constexpr int stages_for(bool throughput) {
+    const int budget = (throughput && BN <= 128 ? 72 : 108) * 1024;
+    return budget / STAGE_BYTES > 8 ? 8 : budget / STAGE_BYTES;
+  }
+  static constexpr int STAGES_2CTA = stages_for(false);
 };
 
 // Epilogue flavours (compile-time, so that each instantiation carries only its own code: these kernels run every code
@@ -87,7 +94,7 @@ __device__ __forceinline__ float4 gelu4(float4 v) {
 // L2 -> SM operand traffic, which bounds this kernel at every batch size (12 TB/s at 128x128 tiles), drops by a quarter.
 // A ring slot may be refilled only when BOTH CTAs have consumed it: the MMA commit arrives on both CTAs' empty barrier.
 template <int BN, int EPI, bool MC>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 3)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                     const GemmShape shape, const GemmEpilogue ep) {
   using S = GemmSmem<BN>;

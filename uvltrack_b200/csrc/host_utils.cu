@@ -82,11 +82,13 @@ int g_gemm_multicast = [] {
   return (e && e[0] == '1') ? 1 : 0;
 }();
 
-int pick_bn(int M, int N, int groups, bool out_f32) {
+int pick_bn(int M, int N, int groups, bool out_f32, int act) {
   // 128 x 256 tiles halve the A-operand smem reads per FLOP and cut the L2 -> SM operand traffic by a quarter: measured
   // 862 -> 1029 TFLOP/s on the qkv GEMM at M = 16416, but slower for the fp32-output GEMMs (N = 768: only three N tiles,
-  // two-pass epilogue) and whenever the grid is below ~2.5 waves of 2 x 148 CTAs (profiles/r01_gemm_bn256.txt)
-  if (!out_f32 && N % 256 == 0 && static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / 256) * groups >= 740)
+  // two-pass epilogue), for the GELU epilogue (128-wide tiles at three CTAs per SM hide it better) and whenever the grid
+  // is below ~2.5 waves of 2 x 148 CTAs (profiles/r01_gemm_bn256.txt)
+  if (!out_f32 && act == ACT_NONE && N % 256 == 0 &&
+      static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / 256) * groups >= 740)
     return 256;
   // Widest tile that still gives one CTA per SM (148) (measured on B200 at M = 513: wider tiles cut the L2 -> SM operand traffic,
   // which bounds these launches, until fewer than ~2/3 of the SMs have work); below that, the narrowest legal tile.
@@ -122,7 +124,7 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     }
     if (bn == 0) bn = 128;
   }
-  if (bn == 0) bn = pick_bn(M, N, groups, ep.out_f32 != 0);
+  if (bn == 0) bn = pick_bn(M, N, groups, ep.out_f32 != 0, ep.act);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
     set_error("gemm: N must be a multiple of 32");
     return 1;
@@ -148,10 +150,11 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   }
   g->shape = GemmShape{M, N, K, 0, splits};
   {
-    // ring depth: ~100 KB so that two CTAs share an SM (epilogue / mainloop overlap, and PDL residency of the next kernel)
-    const int s2 = bn == 32 ? GemmSmem<32>::STAGES_2CTA : bn == 64 ? GemmSmem<64>::STAGES_2CTA
-                   : bn == 128 ? GemmSmem<128>::STAGES_2CTA : GemmSmem<256>::STAGES_2CTA;
-    g->shape.stages = std::max(std::min(s2, K / GEMM_BK / splits), 1);
+    const long long tiles = static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / bn) * groups * splits;
+    const bool thr = tiles > 2 * 148;  // more than one wave of two CTAs per SM: throughput regime (gemm.cuh)
+    const int st = bn == 32 ? GemmSmem<32>::stages_for(thr) : bn == 64 ? GemmSmem<64>::stages_for(thr)
+                   : bn == 128 ? GemmSmem<128>::stages_for(thr) : GemmSmem<256>::stages_for(thr);
+    g->shape.stages = std::max(std::min(st, K / GEMM_BK / splits), 1);
   }
   g->ep = ep;
   g->bn = bn;

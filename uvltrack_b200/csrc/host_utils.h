@@ -48,7 +48,7 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
 // would leave most SMs idle (small M) and K is long
 int pick_splits(int M, int N, int K);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
-int pick_bn(int M, int N, int groups, bool out_f32);
+int pick_bn(int M, int N, int groups, bool out_f32, int act);
 extern int g_gemm_multicast;  // UVLT_MULTICAST=0 disables the cluster / TMA-multicast GEMM variant
 
 struct AttnLaunch {
