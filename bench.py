@@ -201,7 +201,7 @@ def kernel_rooflines(dims, B, skip_text, pk):
             "per_shape": per, "avg_launch_us": round(g_time / 4 * 1e6, 2)}
     roof_a = {"bound": "tensor", "kernel": "attention_kernel (B=%d, H=%d, n=%d)" % (B, H, n),
               "achieved": round(fa / ta / 1e12, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(fa / ta / 1e12 / peak, 4),
-              "traffic": {(1, 513): 2439424}.get((B, n)), "traffic_note": "ncu --set full, profiles/r01_final_b1_attn_full.md",
+              "traffic": {(1, 513): 2430720}.get((B, n)), "traffic_note": "ncu --set full, profiles/r01_final_b1_attn_full.md",
               "avg_launch_us": round(ta * 1e6, 2)}
     return roof, roof_a
 
