@@ -140,3 +140,17 @@ def test_patch_im2col_uint8_equals_float():
                      xf.reshape(B, 3, 16, 16, 16, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, 256, 768)], dim=1)
     assert torch.equal(outs[0].float(), ref.to(torch.bfloat16).float().reshape(B * Np, 768))
     assert (outs[0].float() - outs[1].float()).abs().max() <= 2.0 ** -6  # at most one bf16 ulp from fp32 op-order
+
+
+def test_gemm_cluster_multicast_variant_matches():
+    """The optional cluster / TMA-multicast GEMM (UVLT_MULTICAST=1, off by default because it measured slower) must stay
+    correct: run the GEMM cases in a subprocess with the variant enabled."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, UVLT_MULTICAST="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k", "test_gemm and not multicast",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

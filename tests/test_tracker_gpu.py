@@ -144,3 +144,23 @@ def test_uint8_fused_preprocess_equals_float_path():
                                  NestedTensor(bt.ids, bt.text_mask), bt.prompt, bt.flag, skip_text=True)
     rows_f = bt.engine.track_decode(bt.window_dev)[:1].cpu().numpy()
     assert np.abs(rows_u8 - rows_f).max() < 1e-5
+
+
+def test_mixed_frame_sizes_fall_back_to_host_preprocessing():
+    """Sequences of one batch may come from videos of different sizes: the device-side crop needs one frame size per
+    call, so such a batch takes the host (OpenCV) path -- with the same boxes as each sequence alone on the device path."""
+    z, x, n = 128, 256, 5
+    dims = ModelDims.base(z, x)
+    sd = synthetic_state_dict(dims, seed=0)
+    params = _params(z, x, "BBOX", sd)
+    a_frames, a_gts = synthetic_sequence(n + 1, seed=61)
+    b_frames, b_gts = synthetic_sequence(n + 1, seed=62, H=360, W=480, box=(200.0, 150.0, 50.0, 60.0))
+    bt = BatchTracker(params, batch=2)
+    bt.initialize([a_frames[0], b_frames[0]], [{"init_bbox": a_gts[0]}, {"init_bbox": b_gts[0]}])
+    mixed = [bt.track([a_frames[t], b_frames[t]]) for t in range(1, n + 1)]
+    single = BatchTracker(params, batch=1, network=bt.network)
+    for k, (frames, gts) in enumerate(((a_frames, a_gts), (b_frames, b_gts))):
+        single.initialize([frames[0]], [{"init_bbox": gts[0]}])
+        for t in range(1, n + 1):
+            box = single.track([frames[t]])[0]["target_bbox"]
+            assert box == mixed[t - 1][k]["target_bbox"], (k, t)

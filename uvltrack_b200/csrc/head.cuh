@@ -357,7 +357,8 @@ __device__ __forceinline__ void masked_softmax(const float* sim, int n, float* o
   __syncthreads();
 }
 
-constexpr int PROMPTER_MAX_N = 2048;  // Nz + Nx <= 2048 (384^2 + 384^2 -> 1152)
+constexpr int PROMPTER_MAX_N = 2048;   // Nz + Nx <= 2048 (384^2 + 384^2 -> 1152)
+constexpr int PROMPTER_SCRATCH = 3072; // floats: bitonic sort buffer (<= PROMPTER_MAX_N), then [3][D] accumulators (D <= 1024)
 
 static __global__ void __launch_bounds__(256) prompter_pool_kernel(const PrompterParams p) {
   pdl_wait();
@@ -369,8 +370,8 @@ static __global__ void __launch_bounds__(256) prompter_pool_kernel(const Prompte
   float* w_tgt = sim + n;                // [n]
   float* w_bgd = w_tgt + n;              // [n]
   float* w_dis = w_bgd + n;              // [n]
-  float* sorted = w_dis + n;             // [PROMPTER_MAX_N]
-  float* red = sorted + PROMPTER_MAX_N;  // [8]
+  float* sorted = w_dis + n;               // [PROMPTER_SCRATCH]
+  float* red = sorted + PROMPTER_SCRATCH;  // [8]
   uint8_t* tmask = reinterpret_cast<uint8_t*>(red + 8);  // [n]
   uint8_t* dmask = tmask + n;                              // [n]
   __shared__ float s_thr;
@@ -463,31 +464,66 @@ static __global__ void __launch_bounds__(256) prompter_pool_kernel(const Prompte
   masked_softmax(sim, n, w_dis, red, 3, tmask, dmask);  // distractors
 
   // ---- three weighted sums over the target rows + query embeddings ----
-  for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int j = 0; j < n; ++j) {
+  // warps stride over the rows (coalesced 16-byte reads of each row), lanes own columns; the per-warp partial sums are
+  // then added in warp order through shared memory (fixed order -> deterministic).  `sorted` is reused as [3][D].
+  {
+    constexpr int MAXV = 8;  // D <= 1024: up to 8 float4 per lane
+    const int nv = p.D / 128;
+    float4 a0[MAXV], a1[MAXV], a2[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) a0[k] = a1[k] = a2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = warp; j < n; j += nwarp) {
       const float* row = (j < p.Nz) ? xb + static_cast<long long>(1 + j) * p.D
                                     : xc + static_cast<long long>(1 + p.Nz + (j - p.Nz)) * p.D;
-      const float v = row[i];
-      a0 += w_tgt[j] * v;
-      a1 += w_dis[j] * v;
-      a2 += w_bgd[j] * v;
+      const float wt = w_tgt[j], wd = w_dis[j], wb = w_bgd[j];
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        if (k < nv) {
+          const float4 v = *reinterpret_cast<const float4*>(row + k * 128 + lane * 4);
+          a0[k].x += wt * v.x; a0[k].y += wt * v.y; a0[k].z += wt * v.z; a0[k].w += wt * v.w;
+          a1[k].x += wd * v.x; a1[k].y += wd * v.y; a1[k].z += wd * v.z; a1[k].w += wd * v.w;
+          a2[k].x += wb * v.x; a2[k].y += wb * v.y; a2[k].z += wb * v.z; a2[k].w += wb * v.w;
+        }
+      }
     }
-    const float q0 = p.query_embed[i] + tok[i];
-    const float q1 = p.query_embed[p.D + i];
-    const float q2 = p.query_embed[2 * p.D + i];
-    const long long o = (static_cast<long long>(b) * 3) * p.D + i;
-    p.src0[o] = q0; p.src0[o + p.D] = q1; p.src0[o + 2 * p.D] = q2;
-    const float s0 = a0 + q0, s1 = a1 + q1, s2 = a2 + q2;
-    p.src[o] = s0; p.src[o + p.D] = s1; p.src[o + 2 * p.D] = s2;
-    p.src_bf16[o] = __float2bfloat16(s0);
-    p.src_bf16[o + p.D] = __float2bfloat16(s1);
-    p.src_bf16[o + 2 * p.D] = __float2bfloat16(s2);
+    float* acc = sorted;  // [3][D] (PROMPTER_SCRATCH floats)
+    __syncthreads();
+    for (int w = 0; w < nwarp; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+          if (k < nv) {
+            float4* d0 = reinterpret_cast<float4*>(acc + k * 128 + lane * 4);
+            float4* d1 = reinterpret_cast<float4*>(acc + p.D + k * 128 + lane * 4);
+            float4* d2 = reinterpret_cast<float4*>(acc + 2 * p.D + k * 128 + lane * 4);
+            if (w == 0) { *d0 = a0[k]; *d1 = a1[k]; *d2 = a2[k]; }
+            else {
+              float4 t = *d0; t.x += a0[k].x; t.y += a0[k].y; t.z += a0[k].z; t.w += a0[k].w; *d0 = t;
+              t = *d1; t.x += a1[k].x; t.y += a1[k].y; t.z += a1[k].z; t.w += a1[k].w; *d1 = t;
+              t = *d2; t.x += a2[k].x; t.y += a2[k].y; t.z += a2[k].z; t.w += a2[k].w; *d2 = t;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+      const float q0 = p.query_embed[i] + tok[i];
+      const float q1 = p.query_embed[p.D + i];
+      const float q2 = p.query_embed[2 * p.D + i];
+      const long long o = (static_cast<long long>(b) * 3) * p.D + i;
+      p.src0[o] = q0; p.src0[o + p.D] = q1; p.src0[o + 2 * p.D] = q2;
+      const float s0 = acc[i] + q0, s1 = acc[p.D + i] + q1, s2 = acc[2 * p.D + i] + q2;
+      p.src[o] = s0; p.src[o + p.D] = s1; p.src[o + 2 * p.D] = s2;
+      p.src_bf16[o] = __float2bfloat16(s0);
+      p.src_bf16[o + p.D] = __float2bfloat16(s1);
+      p.src_bf16[o + 2 * p.D] = __float2bfloat16(s2);
+    }
   }
 }
 
 inline size_t prompter_smem_bytes(int D, int n) {
-  return sizeof(float) * (static_cast<size_t>(D) + 4 * n + PROMPTER_MAX_N + 8) + 2 * static_cast<size_t>(n) + 16;
+  return sizeof(float) * (static_cast<size_t>(D) + 4 * n + PROMPTER_SCRATCH + 8) + 2 * static_cast<size_t>(n) + 16;
 }
 
 // switcher of heads/utils.py:93-97: [src, src_, src][flag]
