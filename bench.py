@@ -171,14 +171,25 @@ def kernel_rooflines(dims, B, skip_text, pk):
         return e0.elapsed_time(e1) * 1e-3 / reps
 
     g_time, g_flops, per = 0.0, 0.0, {}
+    import ctypes as C
+    partials = torch.zeros(3, M, D, device=dev)
+    used = C.c_int(1)
     for name, N_, K_, act, f32 in shapes:
-        def fn(N_=N_, K_=K_, act=act, f32=f32):
+        def fn(N_=N_, K_=K_, act=act, f32=f32, name=name):
+            if name == "fc2":
+                # the engine's own fc2 launch: split-K at small batch (the partials are summed by the next LayerNorm)
+                _cabi.check(lib.uvlt_op_gemm_splitk(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out_f.data_ptr(),
+                                                    out_f.data_ptr(), partials.data_ptr(), M, N_, K_, 0, C.byref(used),
+                                                    _cabi.current_stream()), "uvlt_op_gemm_splitk")
+                return
             _cabi.check(lib.uvlt_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), out_f.data_ptr() if f32 else None,
                                          out_f.data_ptr() if f32 else out_b.data_ptr(), M, N_, K_, act, f32, 0,
                                          _cabi.current_stream()), "uvlt_op_gemm")
         t = timed(fn)
         fl = 2.0 * M * N_ * K_
         per[name] = {"us": round(t * 1e6, 2), "tflops": round(fl / t / 1e12, 1)}
+        if name == "fc2":
+            per[name]["splits"] = int(used.value)
         g_time += t
         g_flops += fl
 

@@ -201,6 +201,13 @@ UVLT_API int uvlt_last_launch_count(uvlt_handle h);
 UVLT_API int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* resid, void* out, int M, int N, int K,
                  int act, int out_f32, int bn, void* stream);
 
+/* The engine's small-batch fc2 configuration: out[M,N] (fp32, may alias resid) = A @ W^T + bias + resid with K cut in
+ * `splits` ranges (0 = the engine's own choice for this shape); split s > 0 writes its raw partial product to
+ * partials + (s-1)*M*N and the consumer adds them (the engine's next LayerNorm does).  *splits_used (may be NULL)
+ * receives the number of splits. */
+UVLT_API int uvlt_op_gemm_splitk(const void* A, const void* W, const float* bias, const float* resid, float* out,
+                                 float* partials, int M, int N, int K, int splits, int* splits_used, void* stream);
+
 /* groups independent GEMMs (the four conv towers): A [G][M,K], W [G][N,K], bias [G][N],
  * out bf16 at out + g*out_gstride + row*out_ld. */
 UVLT_API int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,

@@ -154,3 +154,35 @@ def test_gemm_cluster_multicast_variant_matches():
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k", "test_gemm and not multicast",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("M,splits", [(513, 4), (513, 0), (1026, 2), (4104, 0)])
+def test_gemm_split_k(M, splits):
+    """fc2 at small batch: K is cut in `splits` CTAs per tile; split 0 carries bias + residual, the other splits leave raw
+    fp32 partials that the consumer (the engine's next LayerNorm) adds in a fixed order."""
+    import ctypes as C
+
+    lib = _cabi.load()
+    torch.manual_seed(2)
+    N, K = 768, 3072
+    A = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    R = torch.randn(M, N, device="cuda")
+    out = R.clone()
+    partials = torch.full((3, M, N), float("nan"), device="cuda")
+    used = C.c_int(0)
+    _cabi.check(lib.uvlt_op_gemm_splitk(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), out.data_ptr(),
+                                        partials.data_ptr(), M, N, K, splits, C.byref(used), None))
+    torch.cuda.synchronize()
+    s = used.value
+    assert s == (splits or s) and 1 <= s <= 4
+    if splits == 0:
+        assert s == (4 if M == 513 else 1)     # the engine's rule: split only when the grid would leave SMs idle
+    total = out.clone()
+    for i in range(s - 1):
+        total = total + partials[i]            # same order as the LayerNorm kernel
+    ref = A.float() @ W.float().t() + bias + R
+    assert rel(total, ref) < 2e-5
+    if s < 4:
+        assert torch.isnan(partials[s - 1:]).all()   # untouched

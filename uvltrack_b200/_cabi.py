@@ -68,6 +68,7 @@ SIGNATURES = {
     "uvlt_upload_frames": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "uvlt_op_gemm_splitk": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, C.POINTER(c_int), _P]),
     "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,
                                      c_int, _P]),
     "uvlt_op_attention": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),

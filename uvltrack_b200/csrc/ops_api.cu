@@ -31,6 +31,27 @@ int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* r
   return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 
+int uvlt_op_gemm_splitk(const void* A, const void* W, const float* bias, const float* resid, float* out, float* partials,
+                        int M, int N, int K, int splits, int* splits_used, void* stream) {
+  if (init_kernel_attributes()) return 1;
+  if (splits == 0) splits = pick_splits(M, N, K);
+  GemmEpilogue ep{};
+  ep.bias = bias;
+  ep.resid = resid;
+  ep.resid_ld = N;
+  ep.act = ACT_NONE;
+  ep.out = out;
+  ep.out_f32 = 1;
+  ep.out_ld = N;
+  ep.split_out = partials;
+  ep.split_stride = static_cast<long long>(M) * N;
+  GemmLaunch g;
+  if (gemm_prepare(&g, A, K, 0, W, K, 0, M, N, K, 1, splits > 1 ? 128 : 0, ep, splits)) return 1;
+  if (gemm_launch(g, static_cast<cudaStream_t>(stream))) return 1;
+  if (splits_used) *splits_used = splits;
+  return 0;
+}
+
 int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,
                          int act, long long out_ld, long long out_gstride, int bn, void* stream) {
   if (init_kernel_attributes()) return 1;
