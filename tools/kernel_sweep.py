@@ -91,7 +91,30 @@ def ln(Bs, n=513, D=768):
               flush=True)
 
 
+def splitk(Bs, n=513, D=768):
+    """fp32-output split-K GEMMs: the ViT fc2 shape and the head's first conv GEMM, (BN, splits) grid."""
+    for B in Bs:
+        for name, M, N_, K_, grid in (("fc2", B * n, D, 4 * D, (1, 2, 3, 4, 6, 8)),
+                                      ("head0", B * 256, 1024, 9 * D, (1, 2, 4, 6, 9, 12))):
+            a = torch.randn(M, K_, device="cuda").to(torch.bfloat16)
+            w = (torch.randn(N_, K_, device="cuda") * 0.02).to(torch.bfloat16)
+            out = torch.zeros(M, N_, device="cuda")
+            part = torch.zeros(max(grid), M, N_, device="cuda")
+            used = C.c_int(0)
+            for bn in (32, 64, 128):
+                os.environ["UVLT_SPLITK_BN"] = str(bn)
+                row = []
+                for sp in grid:
+                    def fn():
+                        _cabi.check(lib.uvlt_op_gemm_splitk(a.data_ptr(), w.data_ptr(), None, None, out.data_ptr(),
+                                                            part.data_ptr(), M, N_, K_, sp, C.byref(used),
+                                                            _cabi.current_stream()), "splitk")
+                    row.append(f"s{sp}: {timed(fn) * 1e6:6.2f}")
+                print(f"B={B:3d} {name:5s} M={M:5d} N={N_:5d} K={K_:5d} bn{bn:3d} | " + " | ".join(row) + " us", flush=True)
+            os.environ.pop("UVLT_SPLITK_BN", None)
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     Bs = [int(x) for x in sys.argv[2:]] or [1, 32]
-    {"gemm": gemm, "attn": attn, "ln": ln}[which](Bs)
+    {"gemm": gemm, "attn": attn, "ln": ln, "splitk": splitk}[which](Bs)

@@ -99,7 +99,9 @@ struct uvlt_engine {
 
   // activations
   float* x = nullptr;
-  float* xpart = nullptr;  // [3][B, N, D] split-K partial products of fc2 (same offsets as x)
+  float* xpart = nullptr;  // [splits - 1][B, N, D] split-K partial products of fc2 (same offsets as x)
+  float* head_part = nullptr;  // [head0_splits][B*SS, 4C] raw partial products of the head's first conv GEMM
+  int head0_splits = 1;        // > 1 only for small max_batch (the GEMM is 16 tiles of 108 k-blocks at B = 1)
   float* text_cache = nullptr;  // [B, T, D] text rows after the last BERT-only layer (constant per sequence)
   int text_cache_batch = 0;
   __nv_bfloat16 *a = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *pcol = nullptr;
@@ -153,7 +155,9 @@ int alloc_activations(uvlt_engine* e) {
   const size_t B = e->Bm, N = e->N, D = e->D, Hd = e->Hd, T = e->T, SS = e->SS, C = e->C;
   if (dalloc(e, &e->x, B * N * D)) return 1;
   ENG_CUDA(cudaMemset(e->x, 0, B * N * D * sizeof(float)));
-  if (dalloc(e, &e->xpart, 3 * B * N * D) || dalloc(e, &e->text_cache, B * T * D)) return 1;
+  const int max_sk = std::max(std::max(pick_splits(e->Bm * e->N, e->D, e->Hd), pick_splits(e->Bm * e->Nv, e->D, e->Hd)),
+                              pick_splits(e->Bm * e->T, e->D, e->Hd));
+  if (dalloc(e, &e->xpart, (max_sk - 1) * B * N * D) || dalloc(e, &e->text_cache, B * T * D)) return 1;
   if (dalloc(e, &e->a, B * N * D) || dalloc(e, &e->qkv, B * N * 3 * D) || dalloc(e, &e->att, B * N * D) ||
       dalloc(e, &e->hid, B * N * Hd) || dalloc(e, &e->pcol, B * (e->Nz + e->Nx) * 768))
     return 1;
@@ -165,6 +169,8 @@ int alloc_activations(uvlt_engine* e) {
     return 1;
   const size_t cin[4] = {D, C, C / 2, C / 4};
   const size_t cout[4] = {C, C / 2, C / 4, C / 8};
+  e->head0_splits = pick_head_splits(static_cast<int>(B * SS), static_cast<int>(4 * C), static_cast<int>(9 * D));
+  if (e->head0_splits > 1 && dalloc(e, &e->head_part, e->head0_splits * B * SS * 4 * C)) return 1;
   for (int l = 0; l < 4; ++l) {
     if (dalloc(e, &e->col[l], (l == 0 ? 1 : 4) * B * SS * 9 * cin[l])) return 1;
     if (dalloc(e, &e->y[l], B * SS * 4 * cout[l])) return 1;
@@ -436,7 +442,7 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
     // does not depend on how many sequences share the call (the reduction order is part of the result).
     const int sk = (e->no_splitk || i == e->L - 1) ? 1 : pick_splits(e->Bm * rows, D, Hd);
     p->vit_fc2_splits[i] = sk;
-    if (gemm_prepare(&lp.fc2, e->hid, Hd, 0, w.fc2_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 128 : e->force_bn,
+    if (gemm_prepare(&lp.fc2, e->hid, Hd, 0, w.fc2_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 64 : e->force_bn,
                      ep_stream(e, w.fc2_b, rows, 0), sk))
       return nullptr;
     if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0))
@@ -453,7 +459,7 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
       if (prep(e, &lp.fc1, e->t_a, w.in_w, M, Hd, D, ep_bf16(w.in_b, e->t_hid, Hd, ACT_GELU))) return nullptr;
       const int sk = e->no_splitk ? 1 : pick_splits(e->Bm * T, D, Hd);
       p->bert_fc2_splits = sk;
-      if (gemm_prepare(&lp.fc2, e->t_hid, Hd, 0, w.out_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 128 : e->force_bn,
+      if (gemm_prepare(&lp.fc2, e->t_hid, Hd, 0, w.out_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 64 : e->force_bn,
                        ep_stream(e, w.out_b, T, Nv), sk))
         return nullptr;
     }
@@ -464,8 +470,21 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
     const int cin[4] = {D, C, C / 2, C / 4};
     const int cout[4] = {C, C / 2, C / 4, C / 8};
     // layer 0: one GEMM, the four towers concatenated along N
-    if (prep(e, &p->head[0], e->col[0], e->head_w[0], M, 4 * C, 9 * D, ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU)))
+    const int hs = e->no_splitk ? 1 : e->head0_splits;
+    if (hs > 1) {
+      // every split writes a raw fp32 partial; splitk_reduce_kernel adds them, the bias and the ReLU (run_head)
+      GemmEpilogue ep{};
+      ep.out = e->head_part;
+      ep.out_f32 = 1;
+      ep.out_ld = 4 * C;
+      ep.split_out = e->head_part + static_cast<long long>(e->Bm) * e->SS * 4 * C;
+      ep.split_stride = static_cast<long long>(e->Bm) * e->SS * 4 * C;
+      if (gemm_prepare(&p->head[0], e->col[0], 9 * D, 0, e->head_w[0], 9 * D, 0, M, 4 * C, 9 * D, 1, 64, ep, hs))
+        return nullptr;
+    } else if (prep(e, &p->head[0], e->col[0], e->head_w[0], M, 4 * C, 9 * D,
+                    ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU))) {
       return nullptr;
+    }
     for (int l = 1; l < 4; ++l) {
       GemmEpilogue ep = ep_bf16(e->head_b[l], e->y[l], 4 * cout[l], ACT_RELU);
       ep.bias_gstride = cout[l];
@@ -658,6 +677,19 @@ int run_head(uvlt_engine* e, Plan* p, cudaStream_t s, bool train_branch) {
     if (launch_im2col3x3(ip, s)) { set_error("im2col3x3 launch failed"); return 1; }
     ++e->launch_count;
     RUN(gemm_launch(p->head[l], s));
+    if (l == 0 && p->head[0].shape.splits > 1) {
+      SplitReduceParams rp{};
+      rp.part = e->head_part;
+      rp.stride = static_cast<long long>(e->Bm) * e->SS * 4 * C;
+      rp.splits = p->head[0].shape.splits;
+      rp.bias = e->head_b[0];
+      rp.out = e->y[0];
+      rp.total = static_cast<long long>(B) * e->SS * 4 * C;
+      rp.N = 4 * C;
+      rp.relu = 1;
+      if (launch_splitk_reduce(rp, s)) { set_error("splitk_reduce launch failed"); return 1; }
+      ++e->launch_count;
+    }
   }
   HeadFinalParams hp{};
   hp.y4 = e->y[3]; hp.C4 = C / 8; hp.w5 = e->w5; hp.b5 = e->b5;

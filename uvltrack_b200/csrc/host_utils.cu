@@ -1,5 +1,7 @@
 #include "host_utils.h"
 
+#include <cstdlib>
+
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -104,14 +106,33 @@ int pick_bn(int M, int N, int groups, bool out_f32, int act) {
 }
 
 int pick_splits(int M, int N, int K) {
-  // measured on B200 (tools/kernel_sweep.py): at M = 513 the K = 3072 GEMM takes 17 us unsplit (120 CTAs of 48
-  // k-blocks, L2 -> SM operand traffic bound) and about as long as a K = 768 GEMM when cut in four
+  // measured on B200 (tools/kernel_sweep.py splitk): at M = 513 the K = 3072 GEMM takes 17 us unsplit (L2 -> SM operand
+  // traffic of a few CTAs), 8.1 us cut in four and 7.6 us cut in six with BN = 64 tiles (BN = 128: 9.7 / 9.4); at
+  // M = 1026 four-way is best (9.8 us) and six-way overflows the 3 x 148 resident CTAs (13.5 us)
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  if (N % 128 || K < 2048) return 1;
-  const int tiles = m_tiles * (N / 128);
-  int s = 1;
-  while (s < 4 && tiles * s * 2 <= 148 && K % (GEMM_BK * s * 2) == 0) s *= 2;
-  return s;
+  if (N % 64 || K < 2048 || K % GEMM_BK) return 1;
+  const int tiles = m_tiles * (N / 64);
+  const int kb = K / GEMM_BK;
+  int best = 1;
+  for (int s : {2, 3, 4, 6})
+    if (kb % s == 0 && kb / s >= 8 && tiles * s <= 3 * 148) best = s;
+  return best;
+}
+
+int pick_head_splits(int M, int N, int K) {
+  // the head's first conv GEMM (K = 9 * D): at max_batch 1 it is 32 BN = 64 tiles of 108 k-blocks on 148 SMs (33 us);
+  // cut in nine it takes 8.2 us (+ the reduce kernel).  Smallest split that fills ~2 CTAs per SM, >= 8 k-blocks each.
+  if (const char* v = std::getenv("UVLT_HEAD_SPLITS")) return std::max(1, std::atoi(v));
+  if (N % 64 || K % GEMM_BK) return 1;
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / 64);
+  const int kb = K / GEMM_BK;
+  int best = 1;
+  for (int s = 2; s <= 12; ++s) {
+    if (kb % s || kb / s < 8 || tiles * s > 3 * 148) continue;
+    best = s;
+    if (tiles * s >= 256) break;
+  }
+  return best;
 }
 
 int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstride, const void* W, long long w_ld,
@@ -122,7 +143,7 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
       set_error("gemm: split-K needs an fp32 output, a partial buffer and K % (64 * splits) == 0");
       return 1;
     }
-    if (bn == 0) bn = 128;
+    if (bn == 0) bn = 64;
   }
   if (bn == 0) bn = pick_bn(M, N, groups, ep.out_f32 != 0, ep.act);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {

@@ -47,6 +47,8 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
 // split-K factor for an [M, N, K] fp32-output GEMM whose consumer can add partials: > 1 only when the unsplit grid
 // would leave most SMs idle (small M) and K is long
 int pick_splits(int M, int N, int K);
+// split-K factor of the box head's first conv GEMM (raw partials + splitk_reduce_kernel); 1 = do not split
+int pick_head_splits(int M, int N, int K);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int pick_bn(int M, int N, int groups, bool out_f32, int act);
 extern int g_gemm_multicast;  // UVLT_MULTICAST=0 disables the cluster / TMA-multicast GEMM variant

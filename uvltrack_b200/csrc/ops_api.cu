@@ -1,5 +1,6 @@
 // Operator-level C-ABI entry points (declared in include/uvlt.h).  They exist so that every kernel of the hot path
 // can be parity-tested in isolation against the oracle through the same boundary the engine uses.
+#include <cstdlib>
 #include "../../include/uvlt.h"
 #include "host_utils.h"
 #include "rowwise.cuh"
@@ -46,7 +47,9 @@ int uvlt_op_gemm_splitk(const void* A, const void* W, const float* bias, const f
   ep.split_out = partials;
   ep.split_stride = static_cast<long long>(M) * N;
   GemmLaunch g;
-  if (gemm_prepare(&g, A, K, 0, W, K, 0, M, N, K, 1, splits > 1 ? 128 : 0, ep, splits)) return 1;
+  int bn = splits > 1 ? 64 : 0;
+  if (const char* v = std::getenv("UVLT_SPLITK_BN")) bn = std::atoi(v);  // tools/kernel_sweep.py only
+  if (gemm_prepare(&g, A, K, 0, W, K, 0, M, N, K, 1, bn, ep, splits)) return 1;
   if (gemm_launch(g, static_cast<cudaStream_t>(stream))) return 1;
   if (splits_used) *splits_used = splits;
   return 0;

@@ -392,4 +392,47 @@ inline int launch_build_bias(const BiasParams& p, cudaStream_t s) {
   return cudaGetLastError() != cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// split-K reduction with the epilogue the split GEMM could not apply: out = act(sum_s part[s] + bias), bf16.
+// Partials are added in the fixed order s = 0 .. splits-1 (the result does not depend on the grid).
+// ---------------------------------------------------------------------------------------------------------------
+struct SplitReduceParams {
+  const float* part;      // [splits][M, N]
+  long long stride;       // elements between partials
+  int splits;
+  const float* bias;      // [N] or nullptr
+  __nv_bfloat16* out;     // [M, N]
+  long long total;        // M * N  (N % 4 == 0)
+  int N;
+  int relu;
+};
+
+static __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitReduceParams p) {
+  pdl_wait();
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (i >= p.total) return;
+  float4 acc = *reinterpret_cast<const float4*>(p.part + i);
+  for (int s = 1; s < p.splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(p.part + s * p.stride + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (p.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(p.bias + static_cast<int>(i % p.N));
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (p.relu) {
+    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+  }
+  __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p.out + i) = o;
+}
+inline int launch_splitk_reduce(const SplitReduceParams& p, cudaStream_t s) {
+  const long long threads = p.total / 4;
+  UVLT_LAUNCH(splitk_reduce_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, s, p);
+  return cudaGetLastError() != cudaSuccess;
+}
+
 }  // namespace uvlt
