@@ -197,7 +197,8 @@ UVLT_API int uvlt_last_launch_count(uvlt_handle h);
 
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + resid;  A, W bf16 row-major; bias fp32 [N] or NULL; resid fp32 [M,N]
  * or NULL (may alias out when out_f32); out bf16 or fp32.  nn.Linear semantics (block.py:49,59; utils.py:63-69).
- * bn: tile width 32/64/128, 0 = auto.  Requires K % 64 == 0, N % 32 == 0. */
+ * bn: tile width 32/64/128/256, 0 = auto, 512 = the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tile per pair of
+ * CTAs; needs N % 256 == 0).  Requires K % 64 == 0, N % 32 == 0. */
 UVLT_API int uvlt_op_gemm(const void* A, const void* W, const float* bias, const float* resid, void* out, int M, int N, int K,
                  int act, int out_f32, int bn, void* stream);
 

@@ -22,6 +22,11 @@ def rel(a, b):
     # 128 x 256 tiles (large-M throughput configuration): every epilogue flavour, M tail, two-pass fp32 epilogue
     (1300, 2304, 768, 256, 0, False, False), (1300, 3072, 768, 256, 1, False, False), (1300, 768, 3072, 256, 0, True, True),
     (200, 1024, 128, 256, 2, False, False),
+    # bn = 512: the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 pair tile): every epilogue flavour, odd number of
+    # M tiles (the pair's second CTA is all out of bounds), M tail, one k-block, K longer than the ring
+    (1300, 2304, 768, 512, 0, False, False), (1300, 3072, 768, 512, 1, False, False), (1300, 768, 3072, 512, 0, True, True),
+    (513, 768, 768, 512, 0, True, True), (100, 256, 64, 512, 2, False, False), (17696, 2304, 768, 512, 0, False, False),
+    (256, 1024, 6912, 512, 2, False, False),
 ])
 def test_gemm(M, N, K, bn, act, resid, f32):
     lib = _cabi.load()
@@ -170,19 +175,19 @@ def test_gemm_split_k(M, splits):
     bias = torch.randn(N, device="cuda")
     R = torch.randn(M, N, device="cuda")
     out = R.clone()
-    partials = torch.full((3, M, N), float("nan"), device="cuda")
+    partials = torch.full((5, M, N), float("nan"), device="cuda")
     used = C.c_int(0)
     _cabi.check(lib.uvlt_op_gemm_splitk(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), out.data_ptr(),
                                         partials.data_ptr(), M, N, K, splits, C.byref(used), None))
     torch.cuda.synchronize()
     s = used.value
-    assert s == (splits or s) and 1 <= s <= 4
+    assert s == (splits or s) and 1 <= s <= 6
     if splits == 0:
-        assert s == (4 if M == 513 else 1)     # the engine's rule: split only when the grid would leave SMs idle
+        assert s == (6 if M == 513 else 1)     # the engine's rule: split only when the grid would leave SMs idle
     total = out.clone()
     for i in range(s - 1):
         total = total + partials[i]            # same order as the LayerNorm kernel
     ref = A.float() @ W.float().t() + bias + R
     assert rel(total, ref) < 2e-5
-    if s < 4:
+    if s < 6:
         assert torch.isnan(partials[s - 1:]).all()   # untouched

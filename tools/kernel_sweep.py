@@ -51,7 +51,7 @@ def gemm(Bs, n=513, D=768):
         out_f = torch.zeros(M, D, device="cuda")
         for name, N_, K_, act, f32 in (("qkv", 3 * D, D, 0, 0), ("proj", D, D, 0, 1), ("fc1", Hd, D, 1, 0), ("fc2", D, Hd, 0, 1)):
             row = []
-            for bn in (64, 128, 256, 0):
+            for bn in [int(v) for v in os.environ.get("SWEEP_BNS", "128,256,512,0").split(",")]:
                 def fn():
                     _cabi.check(lib.uvlt_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(),
                                                  out_f.data_ptr() if f32 else None,

@@ -145,7 +145,11 @@ struct TraceBuf {
 #define TRACE_DECL TraceBuf _tb; const bool _tb_on = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
 #define TRACE_PT(tag) do { if (_tb_on) _tb.pt(tag); } while (0)
 #define TRACE_FLUSH() do { if (_tb_on) _tb.flush(); } while (0)
+#define TRACE_PARAMS , TraceBuf& _tb, const bool _tb_on
+#define TRACE_ARGS , _tb, _tb_on
 #else
+#define TRACE_PARAMS
+#define TRACE_ARGS
 #define TRACE_DECL ((void)0)
 #define TRACE_PT(tag) ((void)0)
 #define TRACE_FLUSH() ((void)0)
@@ -229,6 +233,18 @@ __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
+// CTA-pair variant (tcgen05 cta_group::2 pipelines): each CTA of the pair loads into its OWN shared memory, but the
+// complete_tx goes to the mbarrier at this offset in the pair's EVEN CTA (bit 24 of a shared::cluster address selects the
+// CTA of the pair), so that the leader's MMA thread waits on one barrier for both CTAs' operands.
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // thread-block clusters
 // ----------------------------------------------------------------------------------------------
@@ -255,6 +271,19 @@ __device__ __forceinline__ void tmem_relinquish() {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// CTA pair: the same warp of BOTH CTAs executes these; the pair gets the same columns in both SMs' TMEM
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -295,6 +324,24 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// CTA-pair MMA (M = 256 over the two CTAs' A tiles, N over the two CTAs' W halves), issued by the leader CTA only
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
 // (implies tcgen05.fence::before_thread_sync)

@@ -48,6 +48,7 @@ struct GemmShape {
   int M, N, K;
   int stages;  // depth of the smem operand ring (2..GEMM_MAX_STAGES), chosen on the host from the grid size
   int splits;  // K is cut into `splits` equal ranges, one CTA each (blockIdx.z = group * splits + split)
+  int groups;  // read by the persistent CTA-pair kernel only (the one-tile kernels take the group from blockIdx.z)
 };
 
 constexpr int GEMM_MAX_STAGES = 12;
@@ -87,6 +88,149 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_RELU = 2, EPI_F32 = 3 };
 __device__ __forceinline__ float4 gelu4(float4 v) {
   v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   return v;
+}
+
+// Epilogue of one 128 x BN accumulator tile, run by the four epilogue warps (warp & 3 = TMEM lane quadrant).
+// Stage 1 (thread = accumulator row): TMEM -> registers, + bias (+ activation, -> bf16) -> staging tile in the (now
+// idle) operand ring, 16-byte chunks XOR-swizzled with the row so that both stages are bank-conflict free.
+// Stage 2 (lanes across columns): coalesced residual read / add, store -- whole rows per warp instruction (a
+// row-per-thread store costs 32 L1 wavefronts per instruction instead of 2-4).
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias, uint64_t* acc_bar, uint32_t acc_parity,
+                                              uint32_t tmem_acc, int m0, int n0, int g, int sp, const GemmShape& shape,
+                                              const GemmEpilogue& ep, int warp, int lane TRACE_PARAMS) {
+  const int lane_grp = warp & 3;  // TMEM lane quadrant this warp may access
+  constexpr bool F32 = (EPI == EPI_F32);
+  constexpr int ESZ = F32 ? 4 : 2;            // staged element size: the bf16 flavours convert in stage 1
+  constexpr int PW = (F32 && BN > 128) ? 128 : BN;  // columns per epilogue pass (the staging tile is <= 64 KB)
+  constexpr int NPASS = BN / PW;
+  constexpr int ROWB = PW * ESZ;              // bytes per staged row
+  constexpr int CPR = ROWB / 16;              // 16-byte chunks per staged row
+  constexpr int RPI = 32 / CPR;               // rows covered by one warp instruction in stage 2
+  constexpr int ITERS = 32 / RPI;
+  constexpr int SWZ = (CPR < 8 ? CPR : 8) - 1;  // XOR swizzle of the chunk index with the row, kept inside the row
+  const uint32_t stage_w = smem_u32(smem) + lane_grp * 32 * ROWB;  // this warp's 32 rows of the staging tile
+  const int j2 = lane % CPR;
+  const int col0 = n0 + j2 * (16 / ESZ);
+  const int r_first = m0 + lane_grp * 32 + lane / CPR;  // this lane's rows are r_first + it * RPI
+  // position of the first row inside its sequence / inside the periodic residual table, computed while the mainloop
+  // runs; advanced incrementally afterwards (the periods are >= 8 rows on this path, checked on the host)
+  int seq_q0 = 0, seq_rem0 = r_first, per_rem0 = 0;
+  if (F32) {
+    if (ep.in_rows_per_b > 0) { seq_q0 = r_first / ep.in_rows_per_b; seq_rem0 = r_first - seq_q0 * ep.in_rows_per_b; }
+    if (ep.resid_period > 0) per_rem0 = r_first % ep.resid_period;
+  }
+  mbar_wait(acc_bar, acc_parity);
+  tc_fence_after();
+  if (threadIdx.x == 64) TRACE_PT(0x105);
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; ++pass) {
+  const int col = col0 + pass * PW;
+  int seq_q = seq_q0, seq_rem = seq_rem0, per_rem = per_rem0;
+  {
+    const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + pass * PW;
+    const uint32_t my_row = stage_w + lane * ROWB;
+    uint32_t va[32], vb[32];
+    // 32 accumulator columns: + bias (+ activation, -> bf16) -> swizzled staging row
+    auto stage1 = [&](uint32_t (&v)[32], int c) {
+      if (F32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 4);
+          const int j = ((c >> 2) + q) ^ (lane & SWZ);
+          sts128(my_row + j * 16, __uint_as_float(v[q * 4]) + b4.x, __uint_as_float(v[q * 4 + 1]) + b4.y,
+                 __uint_as_float(v[q * 4 + 2]) + b4.z, __uint_as_float(v[q * 4 + 3]) + b4.w);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 x0 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8);
+          float4 x1 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8 + 4);
+          x0.x += __uint_as_float(v[q * 8]);     x0.y += __uint_as_float(v[q * 8 + 1]);
+          x0.z += __uint_as_float(v[q * 8 + 2]); x0.w += __uint_as_float(v[q * 8 + 3]);
+          x1.x += __uint_as_float(v[q * 8 + 4]); x1.y += __uint_as_float(v[q * 8 + 5]);
+          x1.z += __uint_as_float(v[q * 8 + 6]); x1.w += __uint_as_float(v[q * 8 + 7]);
+          if (EPI == EPI_BF16_GELU) { x0 = gelu4(x0); x1 = gelu4(x1); }
+          if (EPI == EPI_BF16_RELU) {
+            x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+            x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+          }
+          const int j = ((c >> 3) + q) ^ (lane & SWZ);
+          sts128(my_row + j * 16, __uint_as_float(pack_bf16x2(x0.x, x0.y)), __uint_as_float(pack_bf16x2(x0.z, x0.w)),
+                 __uint_as_float(pack_bf16x2(x1.x, x1.y)), __uint_as_float(pack_bf16x2(x1.z, x1.w)));
+        }
+      }
+    };
+    tmem_ld32(t_row, va);
+    tmem_wait_ld_dep(va);
+#pragma unroll 1
+    for (int c = 0; c < PW; c += 64) {
+      if (c + 32 < PW) tmem_ld32(t_row + c + 32, vb);
+      stage1(va, c);
+      if (c + 32 < PW) {
+        tmem_wait_ld_dep(vb);
+        if (c + 64 < PW) tmem_ld32(t_row + c + 64, va);
+        stage1(vb, c + 32);
+        if (c + 64 < PW) tmem_wait_ld_dep(va);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (threadIdx.x == 64) TRACE_PT(0x108);
+  {
+    const int rows_left = shape.M - r_first;
+    const uint32_t src = stage_w + (lane / CPR) * ROWB;
+    constexpr int UN = ITERS < 4 ? ITERS : 4;
+#pragma unroll 1
+    for (int it0 = 0; it0 < ITERS; it0 += UN) {
+      float4 v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int row_l = (it0 + u) * RPI + lane / CPR;
+        v[u] = lds128(src + (it0 + u) * RPI * ROWB + ((j2 ^ (row_l & SWZ)) * 16));
+      }
+      if (F32) {
+        long long orow[UN];
+        float4 r4[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const bool ok = (it0 + u) * RPI < rows_left;
+          if (ep.in_rows_per_b > 0) {
+            if (seq_rem >= ep.in_rows_per_b) { seq_rem -= ep.in_rows_per_b; ++seq_q; }
+            orow[u] = static_cast<long long>(seq_q) * ep.out_rows_per_b + ep.out_row_off + seq_rem;
+          } else {
+            orow[u] = seq_rem;
+          }
+          seq_rem += RPI;
+          long long rr = orow[u];
+          if (ep.resid_period > 0) {
+            if (per_rem >= ep.resid_period) per_rem -= ep.resid_period;
+            rr = per_rem;
+            per_rem += RPI;
+          }
+          r4[u] = (ep.resid && ok && sp == 0) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if ((it0 + u) * RPI >= rows_left) continue;
+          v[u].x += r4[u].x; v[u].y += r4[u].y; v[u].z += r4[u].z; v[u].w += r4[u].w;
+          float* const obase = sp == 0 ? reinterpret_cast<float*>(ep.out) : ep.split_out + (sp - 1) * ep.split_stride;
+          *reinterpret_cast<float4*>(obase + g * ep.out_gstride + orow[u] * ep.out_ld + col) = v[u];
+        }
+      } else {
+        __nv_bfloat16* const o = reinterpret_cast<__nv_bfloat16*>(ep.out) + g * ep.out_gstride + col;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if ((it0 + u) * RPI >= rows_left) continue;
+          *reinterpret_cast<float4*>(o + static_cast<long long>(r_first + (it0 + u) * RPI) * ep.out_ld) = v[u];
+        }
+      }
+    }
+  }
+  __syncwarp();  // stage 2 has read this pass before the next pass overwrites the staging rows
+  }  // pass
 }
 
 // MC (launched as clusters of two CTAs along N): the two CTAs compute neighbouring N tiles of the same M tile, so they
@@ -217,142 +361,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     // ---------------- epilogue warps ----------------
-    // Stage 1 (thread = accumulator row): TMEM -> registers, + bias -> fp32 staging tile in the (now idle) operand
-    // ring, 16-byte chunks XOR-swizzled with the row so that both stages are bank-conflict free.
-    // Stage 2 (lanes across columns): activation, coalesced residual read / add, convert, store -- whole rows per warp
-    // instruction (a row-per-thread store costs 32 L1 wavefronts per instruction instead of 2-4).
-    const int lane_grp = warp & 3;  // TMEM lane quadrant this warp may access
-    constexpr bool F32 = (EPI == EPI_F32);
-    constexpr int ESZ = F32 ? 4 : 2;            // staged element size: the bf16 flavours convert in stage 1
-    constexpr int PW = (F32 && BN > 128) ? 128 : BN;  // columns per epilogue pass (the staging tile is <= 64 KB)
-    constexpr int NPASS = BN / PW;
-    constexpr int ROWB = PW * ESZ;              // bytes per staged row
-    constexpr int CPR = ROWB / 16;              // 16-byte chunks per staged row
-    constexpr int RPI = 32 / CPR;               // rows covered by one warp instruction in stage 2
-    constexpr int ITERS = 32 / RPI;
-    constexpr int SWZ = (CPR < 8 ? CPR : 8) - 1;  // XOR swizzle of the chunk index with the row, kept inside the row
-    const uint32_t stage_w = smem_u32(smem) + lane_grp * 32 * ROWB;  // this warp's 32 rows of the staging tile
-    const int j2 = lane % CPR;
-    const int col0 = n0 + j2 * (16 / ESZ);
-    const int r_first = m0 + lane_grp * 32 + lane / CPR;  // this lane's rows are r_first + it * RPI
-    // position of the first row inside its sequence / inside the periodic residual table, computed while the mainloop
-    // runs; advanced incrementally afterwards (the periods are >= 8 rows on this path, checked on the host)
-    int seq_q0 = 0, seq_rem0 = r_first, per_rem0 = 0;
-    if (F32) {
-      if (ep.in_rows_per_b > 0) { seq_q0 = r_first / ep.in_rows_per_b; seq_rem0 = r_first - seq_q0 * ep.in_rows_per_b; }
-      if (ep.resid_period > 0) per_rem0 = r_first % ep.resid_period;
-    }
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    if (threadIdx.x == 64) TRACE_PT(0x105);
-#pragma unroll 1
-    for (int pass = 0; pass < NPASS; ++pass) {
-    const int col = col0 + pass * PW;
-    int seq_q = seq_q0, seq_rem = seq_rem0, per_rem = per_rem0;
-    {
-      const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + pass * PW;
-      const uint32_t my_row = stage_w + lane * ROWB;
-      uint32_t va[32], vb[32];
-      // 32 accumulator columns: + bias (+ activation, -> bf16) -> swizzled staging row
-      auto stage1 = [&](uint32_t (&v)[32], int c) {
-        if (F32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 4);
-            const int j = ((c >> 2) + q) ^ (lane & SWZ);
-            sts128(my_row + j * 16, __uint_as_float(v[q * 4]) + b4.x, __uint_as_float(v[q * 4 + 1]) + b4.y,
-                   __uint_as_float(v[q * 4 + 2]) + b4.z, __uint_as_float(v[q * 4 + 3]) + b4.w);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 x0 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8);
-            float4 x1 = *reinterpret_cast<const float4*>(s_bias + pass * PW + c + q * 8 + 4);
-            x0.x += __uint_as_float(v[q * 8]);     x0.y += __uint_as_float(v[q * 8 + 1]);
-            x0.z += __uint_as_float(v[q * 8 + 2]); x0.w += __uint_as_float(v[q * 8 + 3]);
-            x1.x += __uint_as_float(v[q * 8 + 4]); x1.y += __uint_as_float(v[q * 8 + 5]);
-            x1.z += __uint_as_float(v[q * 8 + 6]); x1.w += __uint_as_float(v[q * 8 + 7]);
-            if (EPI == EPI_BF16_GELU) { x0 = gelu4(x0); x1 = gelu4(x1); }
-            if (EPI == EPI_BF16_RELU) {
-              x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
-              x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
-            }
-            const int j = ((c >> 3) + q) ^ (lane & SWZ);
-            sts128(my_row + j * 16, __uint_as_float(pack_bf16x2(x0.x, x0.y)), __uint_as_float(pack_bf16x2(x0.z, x0.w)),
-                   __uint_as_float(pack_bf16x2(x1.x, x1.y)), __uint_as_float(pack_bf16x2(x1.z, x1.w)));
-          }
-        }
-      };
-      tmem_ld32(t_row, va);
-      tmem_wait_ld_dep(va);
-#pragma unroll 1
-      for (int c = 0; c < PW; c += 64) {
-        if (c + 32 < PW) tmem_ld32(t_row + c + 32, vb);
-        stage1(va, c);
-        if (c + 32 < PW) {
-          tmem_wait_ld_dep(vb);
-          if (c + 64 < PW) tmem_ld32(t_row + c + 64, va);
-          stage1(vb, c + 32);
-          if (c + 64 < PW) tmem_wait_ld_dep(va);
-        }
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (threadIdx.x == 64) TRACE_PT(0x108);
-    {
-      const int rows_left = shape.M - r_first;
-      const uint32_t src = stage_w + (lane / CPR) * ROWB;
-      constexpr int UN = ITERS < 4 ? ITERS : 4;
-#pragma unroll 1
-      for (int it0 = 0; it0 < ITERS; it0 += UN) {
-        float4 v[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          const int row_l = (it0 + u) * RPI + lane / CPR;
-          v[u] = lds128(src + (it0 + u) * RPI * ROWB + ((j2 ^ (row_l & SWZ)) * 16));
-        }
-        if (F32) {
-          long long orow[UN];
-          float4 r4[UN];
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            const bool ok = (it0 + u) * RPI < rows_left;
-            if (ep.in_rows_per_b > 0) {
-              if (seq_rem >= ep.in_rows_per_b) { seq_rem -= ep.in_rows_per_b; ++seq_q; }
-              orow[u] = static_cast<long long>(seq_q) * ep.out_rows_per_b + ep.out_row_off + seq_rem;
-            } else {
-              orow[u] = seq_rem;
-            }
-            seq_rem += RPI;
-            long long rr = orow[u];
-            if (ep.resid_period > 0) {
-              if (per_rem >= ep.resid_period) per_rem -= ep.resid_period;
-              rr = per_rem;
-              per_rem += RPI;
-            }
-            r4[u] = (ep.resid && ok && sp == 0) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            if ((it0 + u) * RPI >= rows_left) continue;
-            v[u].x += r4[u].x; v[u].y += r4[u].y; v[u].z += r4[u].z; v[u].w += r4[u].w;
-            float* const obase = sp == 0 ? reinterpret_cast<float*>(ep.out) : ep.split_out + (sp - 1) * ep.split_stride;
-            *reinterpret_cast<float4*>(obase + g * ep.out_gstride + orow[u] * ep.out_ld + col) = v[u];
-          }
-        } else {
-          __nv_bfloat16* const o = reinterpret_cast<__nv_bfloat16*>(ep.out) + g * ep.out_gstride + col;
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            if ((it0 + u) * RPI >= rows_left) continue;
-            *reinterpret_cast<float4*>(o + static_cast<long long>(r_first + (it0 + u) * RPI) * ep.out_ld) = v[u];
-          }
-        }
-      }
-    }
-    __syncwarp();  // stage 2 has read this pass before the next pass overwrites the staging rows
-    }  // pass
+    gemm_epilogue<BN, EPI>(smem, s_bias, acc_bar, 0, tmem_acc, m0, n0, g, sp, shape, ep, warp, lane TRACE_ARGS);
     if (threadIdx.x == 64) TRACE_PT(0x106);
   }
 
@@ -361,6 +370,193 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, TMEM_COLS);
+  }
+  if (threadIdx.x == 64) TRACE_PT(0x107);
+  if (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64) TRACE_FLUSH();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair persistent variant (tcgen05 cta_group::2) for the throughput regime.
+//
+// A cluster of two CTAs on the two SMs of a TPC computes 256 x 256 output tiles, one after the other (static
+// round-robin over the grid's clusters).  Each CTA stages its own 128 rows of A and ONE HALF (128 rows) of the W tile
+// per k-block; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads both CTAs'
+// shared memory and writes both CTAs' TMEM (128 lanes x 256 columns each): half the L2 -> SM operand bytes per FLOP of
+// the one-CTA 128 x 128 tile.  The accumulator is double-buffered in TMEM (2 x 256 columns = all of it), so the sixteen
+// epilogue warps drain tile i while the producer / MMA warps are already in the mainloop of tile i + 1, and the
+// per-tile set-up / tear-down latency chains of the one-tile-per-CTA kernel (barrier init, TMEM allocation, pipeline
+// fill, cluster sync: ~8 us per 128 x 256 tile against a 3.3 us mainloop, in-kernel timeline in
+// profiles/r01_gemm_2sm.md) are paid once per kernel.
+//   full_bar[s]      in the LEADER: its producer posts expect_tx for both CTAs' bytes, both CTAs' TMA loads signal it
+//   empty_bar[s]     in each CTA: the leader's tcgen05.commit multicasts the arrive to both
+//   acc_full[b]      in each CTA: multicast commit after the tile's last MMA
+//   acc_empty[b]     in the LEADER: all epilogue warps of the pair arrive once their TMEM reads are done
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GEMM2_BN = 256;       // columns of the pair tile = accumulator columns per CTA and tile
+constexpr int GEMM2_EPI_GROUPS = 4;  // epilogue warp groups (4 warps = the 4 TMEM lane quadrants), 256 / GROUPS columns each
+constexpr int GEMM2_THREADS = 64 + GEMM2_EPI_GROUPS * 128;  // warp 0 TMA, warp 1 MMA, then the epilogue groups
+constexpr int GEMM2_STAGE_BYTES = GEMM_BM * GEMM_BK * 2 + (GEMM2_BN / 2) * GEMM_BK * 2;  // A + half of W: 32 KB
+// each epilogue group stages its 128 x 64 sub-tile (bf16; fp32 in two 32-column passes) in its own 16 KB
+constexpr int GEMM2_GROUP_COLS = GEMM2_BN / GEMM2_EPI_GROUPS;
+constexpr int GEMM2_EPI_BYTES = GEMM2_EPI_GROUPS * GEMM_BM * GEMM2_GROUP_COLS * 2;
+constexpr int GEMM2_MAX_STAGES = 5;
+constexpr int gemm2_smem_bytes(int stages) { return stages * GEMM2_STAGE_BYTES + GEMM2_EPI_BYTES + 256 + 128 * 4; }
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
+gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
+                        const GemmShape shape, const GemmEpilogue ep) {
+  constexpr int BN = GEMM2_BN;
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int STAGE_BYTES = GEMM2_STAGE_BYTES;
+  const int STAGES = shape.stages;
+
+  extern __shared__ __align__(1024) uint8_t gemm_smem[];
+  uint8_t* const smem = gemm_smem;
+  uint8_t* const stage_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + GEMM2_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM2_MAX_STAGES;
+  uint64_t* acc_full = empty_bar + GEMM2_MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_zero = reinterpret_cast<float*>(stage_base + GEMM2_EPI_BYTES + 256);  // bias of a bias-less GEMM
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int num_kb = shape.K / GEMM_BK;
+  const int m_pairs = (shape.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = shape.N / BN;
+  const int tiles_per_group = m_pairs * n_tiles;
+  const int total_tiles = tiles_per_group * shape.groups;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  TRACE_DECL;
+  if (threadIdx.x == 0) TRACE_PT(0x100);
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w);
+#pragma unroll 1
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 2 * 4 * GEMM2_EPI_GROUPS);
+    mbar_init(&acc_empty[1], 2 * 4 * GEMM2_EPI_GROUPS);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 2 * BN);
+    tmem_relinquish_2sm();
+  }
+  if (threadIdx.x < 128) s_zero[threadIdx.x] = 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any TMA / commit can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE_PT(0x101);
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) TRACE_PT(0x102);
+
+  // tile t -> (group, n tile, m pair): m fastest, so the clusters running at the same time share W tiles in L2
+  auto tile_coords = [&](int t, int& g, int& m0, int& n0) {
+    g = t / tiles_per_group;
+    const int r = t - g * tiles_per_group;
+    const int nt = r / m_pairs;
+    m0 = ((r - nt * m_pairs) * 2 + static_cast<int>(crank)) * GEMM_BM;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      int s = 0;
+      uint32_t ph = 1;  // fresh barriers: the first pass over the ring does not wait
+#pragma unroll 1
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        int g, m0, n0;
+        tile_coords(t, g, m0, n0);
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph);  // the leader's MMAs have drained this slot in BOTH CTAs
+          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          tma_load_3d_2sm(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
+          tma_load_3d_2sm(a_dst + A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0 + static_cast<int>(crank) * (BN / 2), g);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      // ---------------- MMA issuer (leader only) ----------------
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+#pragma unroll 1
+      for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (it == 0 && kb < 2) TRACE_PT(0x103);
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc_sw128(a_addr, 1024, 0);
+          const uint64_t bdesc = umma_smem_desc_sw128(a_addr + A_BYTES, 1024, 0);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16_ss_2sm(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s], 0x3);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(&acc_full[buf], 0x3);
+        if (it < 4) TRACE_PT(0x104);
+      }
+    }
+  } else {
+    // ---------------- epilogue: group q (4 warps) owns columns [q * 64, +64) of the tile ----------------
+    constexpr int GC = GEMM2_GROUP_COLS;
+    const int half = (warp - 2) >> 2;
+    uint8_t* const stage = stage_base + half * (GEMM2_EPI_BYTES / GEMM2_EPI_GROUPS);
+    const uint32_t leader_empty = smem_u32(acc_empty) & 0xFEFFFFFFu;  // the pair's even CTA (see tma_load_3d_2sm)
+    int it = 0;
+#pragma unroll 1
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
+      int g, m0, n0;
+      tile_coords(t, g, m0, n0);
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      const uint32_t tmem_acc = tmem_base + buf * BN + half * GC;
+      const int nh = n0 + half * GC;
+      const float* bias = ep.bias ? ep.bias + g * ep.bias_gstride + nh : s_zero;
+      constexpr int CW = (EPI == EPI_F32) ? GC / 2 : GC;  // same staging bytes for fp32 and bf16 rows
+#pragma unroll 1
+      for (int c = 0; c < GC; c += CW)
+        gemm_epilogue<CW, EPI>(stage, bias + c, &acc_full[buf], par, tmem_acc + c, m0, nh + c, g, 0, shape, ep, warp,
+                               lane TRACE_ARGS);
+      // this warp's TMEM reads of the tile are complete (the epilogue ends its stage 1 with a tcgen05 fence)
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty + buf * 8) : "memory");
+      if (threadIdx.x == 64 && it < 4) TRACE_PT(0x106);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may release its TMEM / shared memory while the pair still uses it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
   if (threadIdx.x == 64) TRACE_PT(0x107);
   if (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64) TRACE_FLUSH();

@@ -53,6 +53,8 @@ int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
   return 0;
 }
 
+static int g_num_sms = 148;
+
 int init_kernel_attributes() {
   static int status = -1;
   static std::mutex mu;
@@ -69,9 +71,19 @@ int init_kernel_attributes() {
   UVLT_GEMM_ATTR_BN(64);
   UVLT_GEMM_ATTR_BN(128);
   UVLT_GEMM_ATTR_BN(256);
+#define UVLT_GEMM2_ATTR(EPI)                                                                                    \
+  UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    gemm2_smem_bytes(GEMM2_MAX_STAGES)))
+  UVLT_GEMM2_ATTR(EPI_BF16); UVLT_GEMM2_ATTR(EPI_BF16_GELU); UVLT_GEMM2_ATTR(EPI_BF16_RELU); UVLT_GEMM2_ATTR(EPI_F32);
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
+  {
+    int dev = 0, sms = 0;
+    UVLT_CUDA_OK(cudaGetDevice(&dev));
+    UVLT_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = sms > 1 ? sms : 148;
+  }
   status = 0;
   return 0;
 }
@@ -83,6 +95,32 @@ int g_gemm_multicast = [] {
   const char* e = getenv("UVLT_MULTICAST");
   return (e && e[0] == '1') ? 1 : 0;
 }();
+
+// CTA-pair persistent GEMM (gemm_bf16_tn_2sm_kernel): UVLT_GEMM_2SM=0 never, 1 by the rule below (default), 2 wherever
+// legal.  Measured on B200 (tools/kernel_sweep.py gemm, profiles/r01_gemm_2sm.md), us per GEMM, best one-CTA tile vs pair:
+//   M = 16416: qkv 56.1 -> 49.0, proj 35.5 -> 30.1, fc1 99.5 -> 83.1, fc2 87.4 -> 77.5
+//   M =  8208: qkv 27.3 -> 27.7, proj 17.2 -> 19.6, fc1 53.1 -> 46.7, fc2 42.9 -> 41.2
+//   M =  4104: qkv 19.1 -> 19.2, proj 13.7 -> 13.1, fc1 28.3 -> 26.4, fc2 28.4 -> 24.4       M = 2052: one-CTA tiles win
+// The persistent kernel loses when its last round of tiles leaves most of the 74 TPCs idle (proj at M = 8208: 99 tiles).
+int g_gemm_2sm = [] {
+  const char* e = getenv("UVLT_GEMM_2SM");
+  return e ? std::atoi(e) : 1;
+}();
+static int g_gemm_2sm_stages = [] {
+  const char* e = getenv("UVLT_GEMM_2SM_STAGES");
+  return e ? std::min(std::max(std::atoi(e), 2), GEMM2_MAX_STAGES) : GEMM2_MAX_STAGES;
+}();
+
+static bool use_2sm(int M, int N, int K, int groups, int splits) {
+  if (!g_gemm_2sm || N % GEMM2_BN || splits != 1) return false;
+  if (g_gemm_2sm >= 2) return true;
+  if (M < 4096) return false;
+  const long long m_pairs = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const long long tiles = m_pairs * (N / GEMM2_BN) * groups;
+  const long long clusters = std::min<long long>(tiles, g_num_sms / 2);
+  const long long rounds = (tiles + clusters - 1) / clusters;
+  return K >= 2048 || 4 * tiles >= 3 * rounds * clusters;  // last-round efficiency >= 0.75
+}
 
 int pick_bn(int M, int N, int groups, bool out_f32, int act) {
   // 128 x 256 tiles halve the A-operand smem reads per FLOP and cut the L2 -> SM operand traffic by a quarter: measured
@@ -145,6 +183,15 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     }
     if (bn == 0) bn = 64;
   }
+  g->two_sm = false;
+  if (bn == 512 || (bn == 0 && use_2sm(M, N, K, groups, splits))) {
+    if (N % GEMM2_BN || splits != 1) {
+      set_error("gemm: the CTA-pair kernel needs N % 256 == 0 and no split-K");
+      return 1;
+    }
+    g->two_sm = true;
+    bn = GEMM2_BN;
+  }
   if (bn == 0) bn = pick_bn(M, N, groups, ep.out_f32 != 0, ep.act);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) {
     set_error("gemm: N must be a multiple of 32");
@@ -169,13 +216,13 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     set_error("gemm: row remap / residual periods must be >= 8 rows");
     return 1;
   }
-  g->shape = GemmShape{M, N, K, 0, splits};
+  g->shape = GemmShape{M, N, K, 0, splits, groups};
   {
     const long long tiles = static_cast<long long>((M + GEMM_BM - 1) / GEMM_BM) * (N / bn) * groups * splits;
     const bool thr = tiles > 2 * 148;  // more than one wave of two CTAs per SM: throughput regime (gemm.cuh)
     const int st = bn == 32 ? GemmSmem<32>::stages_for(thr) : bn == 64 ? GemmSmem<64>::stages_for(thr)
                    : bn == 128 ? GemmSmem<128>::stages_for(thr) : GemmSmem<256>::stages_for(thr);
-    g->shape.stages = std::max(std::min(st, K / GEMM_BK / splits), 1);
+    g->shape.stages = g->two_sm ? g_gemm_2sm_stages : std::max(std::min(st, K / GEMM_BK / splits), 1);
   }
   g->ep = ep;
   g->bn = bn;
@@ -183,9 +230,10 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   if (groups == 1) { a_gstride = static_cast<long long>(M) * a_ld; w_gstride = static_cast<long long>(N) * w_ld; }
   if (make_tma_bf16_3d(&g->tma_a, A, K, M, groups, a_ld * 2, a_gstride * 2, GEMM_BM)) return 1;
   // pairs of CTAs along N share the A tile through TMA multicast (64-row halves) whenever the N tiles pair up
-  g->multicast = g_gemm_multicast && ((N / bn) % 2 == 0);
+  g->multicast = !g->two_sm && g_gemm_multicast && ((N / bn) % 2 == 0);
   if (g->multicast && make_tma_bf16_3d(&g->tma_a_half, A, K, M, groups, a_ld * 2, a_gstride * 2, GEMM_BM / 2)) return 1;
-  if (make_tma_bf16_3d(&g->tma_w, W, K, N, groups, w_ld * 2, w_gstride * 2, bn)) return 1;
+  // the CTA-pair kernel stages one 128-row half of the 256-wide W tile per CTA
+  if (make_tma_bf16_3d(&g->tma_w, W, K, N, groups, w_ld * 2, w_gstride * 2, g->two_sm ? GEMM2_BN / 2 : bn)) return 1;
   return 0;
 }
 
@@ -206,7 +254,28 @@ static void gemm_launch_bn(const GemmLaunch& g, dim3 grid, cudaStream_t stream) 
   }
 }
 
+static void gemm_launch_2sm(const GemmLaunch& g, cudaStream_t stream) {
+  // persistent: one CTA pair per TPC (or fewer, when there are fewer 256 x 256 tiles)
+  const long long m_pairs = (g.shape.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const long long tiles = m_pairs * (g.shape.N / GEMM2_BN) * g.groups;
+  const int clusters = static_cast<int>(std::min<long long>(tiles, g_num_sms / 2));
+  const dim3 grid(2 * clusters), block(GEMM2_THREADS);
+#define UVLT_GEMM2_LAUNCH(EPI)                                                                                  \
+  (void)launch_kc(gemm_bf16_tn_2sm_kernel<EPI>, grid, block, gemm2_smem_bytes(g.shape.stages), stream, 2, g.tma_a, \
+                  g.tma_w, g.shape, g.ep)
+  if (g.ep.out_f32) UVLT_GEMM2_LAUNCH(EPI_F32);
+  else if (g.ep.act == ACT_GELU) UVLT_GEMM2_LAUNCH(EPI_BF16_GELU);
+  else if (g.ep.act == ACT_RELU) UVLT_GEMM2_LAUNCH(EPI_BF16_RELU);
+  else UVLT_GEMM2_LAUNCH(EPI_BF16);
+#undef UVLT_GEMM2_LAUNCH
+}
+
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
+  if (g.two_sm) {
+    gemm_launch_2sm(g, stream);
+    UVLT_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(g.shape.N / g.bn, (g.shape.M + GEMM_BM - 1) / GEMM_BM, g.groups * g.shape.splits);
   if (g.multicast) {
     switch (g.bn) {

@@ -34,6 +34,7 @@ struct GemmLaunch {
   CUtensorMap tma_a, tma_w;
   CUtensorMap tma_a_half;  // 64-row boxes of A for the multicast variant
   bool multicast;
+  bool two_sm;  // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 pair tile); bn == 256
   GemmShape shape;
   GemmEpilogue ep;
   int bn;      // 32 / 64 / 128
