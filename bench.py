@@ -359,6 +359,7 @@ def run_b200(a):
     if world > 1:
         dist.barrier()
     e2e_launches = 0
+    h2d0 = tracker.h2d_bytes
     t0 = time.perf_counter()
     for i in range(a.steps):
         res = tracker.track([s[0][a.warmup + 1 + i] for s in seqs])
@@ -398,9 +399,11 @@ def run_b200(a):
                    "vs_baseline_note": "value / 60 FPS = the reference's RTX-3090 profile_model.py figure for UVLTrack-B "
                                        "(z128/x256, forward_test only); this workload is the heavier 256/256 shape"},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s",
-                "h2d_bytes_per_step": int(B * np.prod(seqs[0][0][0].shape)),
+                "h2d_bytes_per_step": int((tracker.h2d_bytes - h2d0) / a.steps),
+                "frame_bytes_per_step": int(B * np.prod(seqs[0][0][0].shape)),
                 "d2h_bytes_per_step": B * 80, "ms_per_step": round(e2e_s / a.steps * 1e3, 4),
-                "path": "BatchTracker.track(): raw uint8 frames (480x640x3) -> pinned staging -> H2D -> "
+                "path": "BatchTracker.track(): raw uint8 frames (480x640x3) -> search window of each frame (the only "
+                        "pixels sample_target reads) -> pinned staging -> H2D -> "
                         "uvlt_track_frame_image_host (device crop+resize bit-exact with cv2, forward_test, window merge, "
                         "map_box_back / clip_box) -> D2H of the [B,10] fp64 rows; prompt update every 20 frames; final "
                         "trajectory all-gather included"},

@@ -182,6 +182,13 @@ UVLT_API int uvlt_track_frame_image_host(uvlt_handle h, const uint8_t* frames_ho
 UVLT_API int uvlt_upload_frames(uvlt_handle h, const uint8_t* host, int64_t dst_offset, int64_t nbytes,
                                 int64_t total_bytes, void* stream);
 
+/* Same, for a sub-rectangle: `rows` rows of `width_bytes` from `host` (row pitch src_pitch) to byte offset dst_offset of
+ * the staging buffer with row pitch dst_pitch (= frame_w * 3).  sample_target only reads the search window
+ * (processing_utils.py:183-199: x1..x2, y1..y2 clipped to the frame), so a caller that knows the box state uploads just
+ * that window of every frame; the rest of the staging buffer is never read by that step. */
+UVLT_API int uvlt_upload_frames_2d(uvlt_handle h, const uint8_t* host, int64_t src_pitch, int64_t dst_offset,
+                                   int64_t dst_pitch, int64_t width_bytes, int64_t rows, int64_t total_bytes, void* stream);
+
 /* sample_target alone (device pointers): frames uint8 [B,H,W,3], state fp64 [B,4] -> crops uint8 [B,S,S,3] and
  * resize_factor fp64 [B] (0 when the crop side is < 1). */
 UVLT_API int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, const double* state,

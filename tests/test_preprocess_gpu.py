@@ -85,3 +85,34 @@ def test_device_and_host_preprocessing_give_the_same_boxes(mode):
             # same crop bytes -> same network outputs -> same fp64 box arithmetic: identical, not merely close
             assert rd[b]["target_bbox"] == rh[b]["target_bbox"], (t, b, rd[b], rh[b])
             assert rd[b]["score"] == rh[b]["score"]
+
+
+def test_window_upload_never_reads_stale_pixels():
+    """track() uploads only the search window of each frame into the device staging buffer; every other pixel there is
+    stale (earlier frames).  With independent noise frames any stale or missing pixel inside the crop changes the crop,
+    hence the box: the device path must still equal the host path (full-frame OpenCV crop) exactly, also with windows
+    that hang over the frame border."""
+    z, x, n = 128, 256, 14
+    dims = ModelDims.base(z, x)
+    cfg = config.baseline_cfg("base", z, x, mode="BBOX")
+    params = config.parameters(cfg)
+    params.state_dict = synthetic_state_dict(dims, seed=0)
+    B = 3
+    rng = np.random.default_rng(7)
+    boxes = [(5.0, 8.0, 50.0, 70.0), (560.0, 400.0, 70.0, 60.0), (300.0, 200.0, 90.0, 30.0)]
+    frames0 = [rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8) for _ in range(B)]
+    infos = [{"init_bbox": list(bx)} for bx in boxes]
+    dev = BatchTracker(params, batch=B, device_preprocess=True)
+    host = BatchTracker(params, batch=B, network=dev.network, device_preprocess=False)
+    dev.initialize(frames0, infos)
+    host.initialize(frames0, infos)
+    uploaded = 0
+    for t in range(1, n + 1):
+        images = [rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8) for _ in range(B)]
+        before = dev.h2d_bytes
+        rd = dev.track(images)
+        uploaded += dev.h2d_bytes - before
+        rh = host.track(images)
+        for b in range(B):
+            assert rd[b]["target_bbox"] == rh[b]["target_bbox"], (t, b, rd[b], rh[b])
+    assert 0 < uploaded < n * B * 480 * 640 * 3  # windows, not whole frames

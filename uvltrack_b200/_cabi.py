@@ -66,6 +66,7 @@ SIGNATURES = {
     "uvlt_op_crop_resize": (c_int, [_P, c_int32, c_int32, _P, C.c_double, c_int32, _P, _P, c_int32, _P]),
     "uvlt_text_encode": (c_int, [_P, _P, _P, _P, c_int32, _P]),
     "uvlt_upload_frames": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P]),
+    "uvlt_upload_frames_2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "uvlt_op_gemm_splitk": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, C.POINTER(c_int), _P]),

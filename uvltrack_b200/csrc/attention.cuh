@@ -49,6 +49,10 @@ struct AttnSmem {
   static constexpr int OFF_P = OFF_V + ATT_STAGES * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int TOTAL = OFF_BAR + 256;  // 65792 B: 3 x (TOTAL + 1 KB reserved) <= 228 KB per SM
+  // key-split variant (cluster of two CTAs per query tile): the partner's partial output lands here
+  static constexpr int OFF_XO = TOTAL;                          // [16 x (128 rows x float4)] = 32 KB, fp32 O partial
+  static constexpr int OFF_XML = OFF_XO + ATT_BQ * ATT_D * 4;   // [128] float2 (reference, row sum)
+  static constexpr int TOTAL_SPLIT = OFF_XML + ATT_BQ * 8;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -99,8 +103,11 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&p
     if (MODE == 2) {
       const float b0 = (i < lim ? __ldg(bias_c + i) : 0.0f) * ATT_LOG2E;
       const float b1 = (i + 1 < lim ? __ldg(bias_c + i + 1) : 0.0f) * ATT_LOG2E;
-      p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale, b0) + neg_m);
-      p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale, b1) + neg_m);
+      // scale and reference in ONE fma exactly as in the unbiased modes, the bias added afterwards: a key whose bias
+      // is 0 gets bit-identical probabilities whichever mode its block runs in (so masking the text keys and dropping
+      // them give the same image rows, engine option skip_text)
+      p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale, neg_m) + b0);
+      p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale, neg_m) + b1);
     } else {
       p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale, neg_m));
       p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale, neg_m));
@@ -129,6 +136,11 @@ __device__ __forceinline__ float chunk_exp_dyn(int mode, const uint32_t (&v)[32]
   return chunk_exp<2>(v, pk, scale, neg_m, bias_c, lim);
 }
 
+// SPLIT (launched as clusters of two CTAs along x, small grids only): the two CTAs of a cluster share one query tile and
+// each takes half of the key blocks -- at batch 1 the kernel is 60 serial per-CTA chains of 9 key blocks on 148 SMs, so
+// halving the chain is worth more than the exchange.  CTA 1 sends its partial (O, reference, row sum) through
+// distributed shared memory; CTA 0 merges the two partial softmaxes exactly and stores.
+template <bool SPLIT>
 static __global__ void __launch_bounds__(ATT_THREADS, 3)
 attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t att_smem[];  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment
@@ -149,11 +161,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BQ;
+  const int q0 = (SPLIT ? (blockIdx.x >> 1) : blockIdx.x) * ATT_BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int D = p.H * ATT_D;
-  const int nblk = (p.n + ATT_BKV - 1) / ATT_BKV;
+  const int nblk = (p.n + ATT_BKV - 1) / ATT_BKV;  // key blocks of the sequence
+  // this CTA's key blocks [jb, je); loop counters below are local (jj = j - jb), masks / tails use the global j
+  const uint32_t crank = SPLIT ? cluster_ctarank() : 0u;
+  const int jb = (SPLIT && crank) ? (nblk + 1) / 2 : 0;
+  const int je = (SPLIT && !crank) ? (nblk + 1) / 2 : nblk;
 
   if (warp == 0 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();  // dynamic shared memory must be 1024-byte aligned
@@ -190,7 +206,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       tma_load_3d(sQ, &tma_q, q_full, h * ATT_D, q0, b);
       int s = 0;
       uint32_t ph = 0;
-      for (int j = 0; j < nblk; ++j) {
+      for (int j = jb; j < je; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
         mbar_expect_tx(&kv_full[s], 2 * AttnSmem::KV_BYTES);
         tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
@@ -227,22 +243,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      issue_qk(0);
+      issue_qk(jb);
       int sv = 0;  // ring stage of the next PV
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
+      for (int j = jb; j < je; ++j) {
+        const int jj = j - jb;
+        if (j + 1 < je) {
           // the softmax warps hold S_j in registers -> overwrite it with S_{j+1} while they compute P_j
           mbar_wait(&kv_full[sq], phq);
-          mbar_wait(s_empty, j & 1);
+          mbar_wait(s_empty, jj & 1);
           tc_fence_after();
           issue_qk(j + 1);
         }
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, jj & 1);
         tc_fence_after();
         const int ksteps = (j == nblk - 1) ? ((last_valid + 15) >> 4) : (ATT_BKV / 16);
         const uint64_t vd = vd_base + KV_STEP * sv;
         const uint64_t pd = pd_base;
-        umma_bf16_ss(tmem_O, pd, vd, idesc_pv, j > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem_O, pd, vd, idesc_pv, jj > 0 ? 1u : 0u);
         if (ksteps > 1) umma_bf16_ss(tmem_O, pd + 2, vd + 128, idesc_pv, 1u);
         if (ksteps > 2) umma_bf16_ss(tmem_O, pd + 4, vd + 256, idesc_pv, 1u);
         if (ksteps > 3) umma_bf16_ss(tmem_O, pd + 6, vd + 384, idesc_pv, 1u);
@@ -273,13 +290,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     float m_run = -INFINITY;  // reference of the running sum / output (scaled log2 domain): the largest score seen,
                               // moved only when the maximum grows by more than 2^8 (P stays <= 256; exact after O / l)
     float l_run = 0.0f;
-    for (int j = 0; j < nblk; ++j) {
+    for (int j = jb; j < je; ++j) {
+      const int jj = j - jb;
       const int kv_valid = min(ATT_BKV, p.n - j * ATT_BKV);
       const int nchunk = (((kv_valid + 15) & ~15) + 31) >> 5;  // 32-key chunks the PV MMA may read: must be written
       const int mode = ((biased >> j) & 1u) ? 2 : (kv_valid < ATT_BKV ? 1 : 0);  // block-uniform
       const float* bj = p.bias ? p.bias + static_cast<long long>(b) * p.n + j * ATT_BKV : nullptr;
       uint32_t v[2][32], pk[16];
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, jj & 1);
       tc_fence_after();
       // one wide TMEM load per block (every load -> wait round trip stalls the lone softmax warp of a scheduler for
       // ~150-200 cycles; three narrow loads per block made the kernel 35 % slower)
@@ -301,9 +319,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const float neg_ref = -ref;
 
       // ---- the P buffer (and O) are free once PV_{j-1} has drained ----
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+      if (jj > 0) mbar_wait(pv_done, (jj - 1) & 1);
       tc_fence_after();
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // bring the running output to the new reference (rare)
+      if (jj > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {  // bring the running output to the new reference (rare)
 #pragma unroll
         for (int c = 0; c < ATT_D; c += 32) {
           uint32_t o[32];
@@ -339,29 +357,76 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       mbar_arrive(p_full);
     }
     // ---------------- epilogue: O / l -> bf16 ----------------
-    mbar_wait(pv_done, (nblk - 1) & 1);
+    mbar_wait(pv_done, (je - jb - 1) & 1);
     tc_fence_after();
     const int q = q0 + row;
-    const float inv_l = 1.0f / l_run;
+    float inv_l = 1.0f / l_run;
+    float a_own = 1.0f, a_peer = 0.0f;
+    uint8_t* const xo = smem + AttnSmem::OFF_XO;
+    if (SPLIT) {
+      if (crank == 1) {
+        // send the partial to CTA 0: chunk-major float4s, so that a warp writes 512 contiguous bytes per instruction
+        uint32_t remote_o, remote_ml;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote_o) : "r"(smem_u32(xo)));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote_ml) : "r"(smem_u32(smem + AttnSmem::OFF_XML)));
 #pragma unroll
-    for (int c = 0; c < ATT_D; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_off + c, o);
-      tmem_wait_ld();
-      if (q < p.n) {
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.n + q) * D + h * ATT_D + c;
+        for (int c = 0; c < ATT_D; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_off + c, o);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + i) = u;
+          for (int i = 0; i < 32; i += 4)
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote_o + (((c + i) >> 2) * ATT_BQ + row) * 16),
+                         "r"(o[i]), "r"(o[i + 1]), "r"(o[i + 2]), "r"(o[i + 3])
+                         : "memory");
+        }
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote_ml + row * 8), "f"(m_run), "f"(l_run) : "memory");
+        tc_fence_before();
+      }
+      cluster_sync_all();  // release (CTA 1's stores) / acquire (CTA 0's loads); every thread of both CTAs takes part
+      if (crank == 0) {
+        const float2 ml = *reinterpret_cast<const float2*>(smem + AttnSmem::OFF_XML + row * 8);
+        const float m = fmaxf(m_run, ml.x);
+        a_own = ex2_approx(m_run - m);
+        a_peer = ex2_approx(ml.x - m);
+        inv_l = 1.0f / (l_run * a_own + ml.y * a_peer);
+      }
+    }
+    if (!SPLIT || crank == 0) {
+#pragma unroll
+      for (int c = 0; c < ATT_D; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tmem_O + lane_off + c, o);
+        tmem_wait_ld();
+        if (SPLIT) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xo + (((c + i) >> 2) * ATT_BQ + row) * 16);
+            o[i] = __float_as_uint(__uint_as_float(o[i]) * a_own + x.x * a_peer);
+            o[i + 1] = __float_as_uint(__uint_as_float(o[i + 1]) * a_own + x.y * a_peer);
+            o[i + 2] = __float_as_uint(__uint_as_float(o[i + 2]) * a_own + x.z * a_peer);
+            o[i + 3] = __float_as_uint(__uint_as_float(o[i + 3]) * a_own + x.w * a_peer);
+          }
+        }
+        if (q < p.n) {
+          __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.n + q) * D + h * ATT_D + c;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + i) = u;
+          }
         }
       }
     }
     tc_fence_before();
+  }
+  if (SPLIT && warp < 2) {  // the producer / MMA warps' share of the exchange barrier
+    __syncwarp();
+    cluster_sync_all();
   }
 
   __syncthreads();

@@ -10,6 +10,7 @@
 //   t_*      the same four for the BERT branch, which runs concurrently on a second stream in layers < fusion_start
 //   col*/y*  im2col and activations of the four conv towers of the box head (token-major, tower-concatenated channels)
 // Weights: bf16 [out, in] row-major (nn.Linear layout == K-major B operand), fp32 biases / LayerNorm affine.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include <cmath>
@@ -889,6 +890,9 @@ int uvlt_create(const uvlt_config* cfg, uvlt_handle* out) {
   }
   auto* e = new uvlt_engine();
   e->cfg = *cfg;
+  // UVLT_SPLITK=0: never split K (every row's result is then bit-identical for every max_batch; used by the tests that
+  // compare engines of different batch capacity).  Same as uvlt_set_option("splitk", 0).
+  if (const char* v = std::getenv("UVLT_SPLITK")) e->no_splitk = (v[0] == '0');
   e->D = cfg->embed_dim; e->H = cfg->num_heads; e->L = cfg->depth; e->Hd = cfg->mlp_hidden;
   e->Hz = cfg->template_size; e->Hx = cfg->search_size;
   e->Nz = (e->Hz / 16) * (e->Hz / 16); e->Nx = (e->Hx / 16) * (e->Hx / 16);
@@ -1170,6 +1174,23 @@ int uvlt_upload_frames(uvlt_handle e, const uint8_t* host, int64_t dst_offset, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s)) return 1;
   ENG_CUDA(cudaMemcpyAsync(e->frame_stage + dst_offset, host, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int uvlt_upload_frames_2d(uvlt_handle e, const uint8_t* host, int64_t src_pitch, int64_t dst_offset, int64_t dst_pitch,
+                          int64_t width_bytes, int64_t rows, int64_t total_bytes, void* stream) {
+  if (!e || !host) { set_error("uvlt_upload_frames_2d: null argument"); return 1; }
+  if (rows == 0 || width_bytes == 0) return 0;
+  if (dst_offset < 0 || rows < 0 || width_bytes < 0 || width_bytes > src_pitch || width_bytes > dst_pitch ||
+      dst_offset + (rows - 1) * dst_pitch + width_bytes > total_bytes) {
+    set_error("uvlt_upload_frames_2d: bad range");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s)) return 1;
+  ENG_CUDA(cudaMemcpy2DAsync(e->frame_stage + dst_offset, static_cast<size_t>(dst_pitch), host,
+                             static_cast<size_t>(src_pitch), static_cast<size_t>(width_bytes), static_cast<size_t>(rows),
+                             cudaMemcpyHostToDevice, s));
   return 0;
 }
 

@@ -54,6 +54,11 @@ int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
 }
 
 static int g_num_sms = 148;
+// UVLT_ATTN_SPLIT=0 disables the key-split cluster variant of the attention kernel (A/B timing)
+static int g_attn_split = [] {
+  const char* e = getenv("UVLT_ATTN_SPLIT");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
 
 int init_kernel_attributes() {
   static int status = -1;
@@ -75,8 +80,12 @@ int init_kernel_attributes() {
   UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     gemm2_smem_bytes(GEMM2_MAX_STAGES)))
   UVLT_GEMM2_ATTR(EPI_BF16); UVLT_GEMM2_ATTR(EPI_BF16_GELU); UVLT_GEMM2_ATTR(EPI_BF16_RELU); UVLT_GEMM2_ATTR(EPI_F32);
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    AttnSmem::TOTAL_SPLIT));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
   {
     int dev = 0, sms = 0;
@@ -322,7 +331,16 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
-  UVLT_LAUNCH(attention_kernel, grid, dim3(ATT_THREADS), AttnSmem::TOTAL, stream, a.tma_qkv, a.tma_kv, a.p);
+  // small grids (every CTA has an SM to itself): two CTAs per query tile, half of the key blocks each
+  const bool split = g_attn_split && static_cast<int>(grid.x * grid.y * grid.z) <= g_num_sms &&
+                     (a.p.n + ATT_BKV - 1) / ATT_BKV >= 2;
+  if (split) {
+    grid.x *= 2;
+    (void)launch_kc(attention_kernel<true>, grid, dim3(ATT_THREADS), AttnSmem::TOTAL_SPLIT, stream, 2, a.tma_qkv, a.tma_kv,
+                    a.p);
+  } else {
+    UVLT_LAUNCH(attention_kernel<false>, grid, dim3(ATT_THREADS), AttnSmem::TOTAL, stream, a.tma_qkv, a.tma_kv, a.p);
+  }
   UVLT_CUDA_OK(cudaGetLastError());
   return 0;
 }

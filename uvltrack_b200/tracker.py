@@ -12,6 +12,7 @@ transformer, the box head, the Hanning-window merge / argmax / gather and the D2
 """
 from __future__ import annotations
 
+import math
 import os
 
 import numpy as np
@@ -147,6 +148,7 @@ class BatchTracker:
         self.frames = None  # pinned uint8 [B, H, W, 3], allocated for the first frame size seen
         self._fast = None   # raw pointers of the per-frame engine call, bound per frame size
         self._pool = None
+        self.h2d_bytes = 0  # bytes of raw frames uploaded by track() so far (search windows only)
         self.skip_text = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -275,13 +277,29 @@ class BatchTracker:
             lib, h = self.engine.lib, self.engine.h
             per = H * W * 3
 
+            factor = float(self.params.search_factor)
+            pitch = W * 3
+
             def stage(b):
-                np.copyto(self.frames_np[b], images[b])
-                if lib.uvlt_upload_frames(h, f["frames_ptr"] + b * per, b * per, per, f["total"], stream):
-                    raise RuntimeError("uvlt_upload_frames failed")
+                # only the search window of the frame is read by sample_target (processing_utils.py:183-199): stage and
+                # upload that rectangle (+2 px of slack for the rounding of the window origin), not the whole frame
+                x, y, w, hh = self.state[b]
+                side = math.ceil(math.sqrt(max(w * hh, 0.0)) * factor)
+                xa = max(int(math.floor(x + 0.5 * w - 0.5 * side)) - 2, 0)
+                ya = max(int(math.floor(y + 0.5 * hh - 0.5 * side)) - 2, 0)
+                xb = min(xa + side + 6, W)
+                yb = min(ya + side + 6, H)
+                if xb <= xa or yb <= ya:
+                    return 0  # window entirely outside the frame: the crop is all padding
+                np.copyto(self.frames_np[b, ya:yb, xa:xb], images[b][ya:yb, xa:xb])
+                off = b * per + ya * pitch + xa * 3
+                if lib.uvlt_upload_frames_2d(h, f["frames_ptr"] + off, pitch, off, pitch, (xb - xa) * 3, yb - ya,
+                                             f["total"], stream):
+                    raise RuntimeError("uvlt_upload_frames_2d failed")
+                return (xb - xa) * 3 * (yb - ya)
 
             if self.B == 1:
-                stage(0)
+                self.h2d_bytes += stage(0)
             else:
                 if self._pool is None:
                     from concurrent.futures import ThreadPoolExecutor
@@ -289,7 +307,7 @@ class BatchTracker:
                     dev = torch.cuda.current_device()
                     self._pool = ThreadPoolExecutor(max_workers=min(8, self.B),
                                                     initializer=lambda: torch.cuda.set_device(dev))
-                list(self._pool.map(stage, range(self.B)))
+                self.h2d_bytes += sum(self._pool.map(stage, range(self.B)))
             rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
                                                  f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
                                                  (2 if self.skip_text else 0) | (4 if self.text_cached else 0),
