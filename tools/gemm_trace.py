@@ -7,12 +7,13 @@ sys.path.insert(0, ROOT)
 from uvltrack_b200 import _cabi
 lib = _cabi.load()
 M, N, K, bn = [int(v) for v in sys.argv[1:5]]
+act = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
 bias = torch.zeros(N, device="cuda")
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
 def fn():
-    _cabi.check(lib.uvlt_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, 0, 0, bn,
+    _cabi.check(lib.uvlt_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, act, 0, bn,
                                  _cabi.current_stream()), "gemm")
 s = torch.cuda.Stream()
 buf = (C.c_ulonglong * (3 * 4096))()

@@ -95,7 +95,9 @@ __device__ __forceinline__ float4 gelu4(float4 v) {
 // idle) operand ring, 16-byte chunks XOR-swizzled with the row so that both stages are bank-conflict free.
 // Stage 2 (lanes across columns): coalesced residual read / add, store -- whole rows per warp instruction (a
 // row-per-thread store costs 32 L1 wavefronts per instruction instead of 2-4).
-template <int BN, int EPI>
+// STAGE1_ONLY: stop after the staging tile is written (the caller stores it with one TMA bulk store; bf16 flavours: the
+// staging layout [128 rows][BN = 64 bf16], 16-byte chunks XOR-swizzled with row % 8, IS the 128B-swizzle TMA layout).
+template <int BN, int EPI, bool STAGE1_ONLY = false>
 __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias, uint64_t* acc_bar, uint32_t acc_parity,
                                               uint32_t tmem_acc, int m0, int n0, int g, int sp, const GemmShape& shape,
                                               const GemmEpilogue& ep, int warp, int lane TRACE_PARAMS) {
@@ -178,6 +180,7 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias
   tc_fence_before();
   __syncwarp();
   if (threadIdx.x == 64) TRACE_PT(0x108);
+  if (STAGE1_ONLY) return;
   {
     const int rows_left = shape.M - r_first;
     const uint32_t src = stage_w + (lane / CPR) * ROWB;
@@ -405,7 +408,7 @@ constexpr int gemm2_smem_bytes(int stages) { return stages * GEMM2_STAGE_BYTES +
 template <int EPI>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                        const GemmShape shape, const GemmEpilogue ep) {
+                        const __grid_constant__ CUtensorMap tma_out, const GemmShape shape, const GemmEpilogue ep) {
   constexpr int BN = GEMM2_BN;
   constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   constexpr int STAGE_BYTES = GEMM2_STAGE_BYTES;
@@ -529,6 +532,13 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
     const int half = (warp - 2) >> 2;
     uint8_t* const stage = stage_base + half * (GEMM2_EPI_BYTES / GEMM2_EPI_GROUPS);
     const uint32_t leader_empty = smem_u32(acc_empty) & 0xFEFFFFFFu;  // the pair's even CTA (see tma_load_3d_2sm)
+    // bf16 flavours: the group's 128 x 64 staging tile goes out with ONE TMA bulk store issued by the group's first
+    // thread -- with sixteen warps pushing row stores through the LSU while the TMA loads saturate the L2 slices, the
+    // store stage alone took ~5k cycles per tile and made the GELU epilogue (7.4k cycles of math) the bound of fc1
+    constexpr bool TMA_ST = (EPI != EPI_F32);
+    const bool store_thread = ((warp - 2) & 3) == 0 && lane == 0;
+    const int bar_id = 1 + half;  // named barrier of this epilogue group (0 is __syncthreads)
+    if (TMA_ST && store_thread) tma_prefetch_desc(&tma_out);
     int it = 0;
 #pragma unroll 1
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
@@ -539,16 +549,35 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       const uint32_t tmem_acc = tmem_base + buf * BN + half * GC;
       const int nh = n0 + half * GC;
       const float* bias = ep.bias ? ep.bias + g * ep.bias_gstride + nh : s_zero;
-      constexpr int CW = (EPI == EPI_F32) ? GC / 2 : GC;  // same staging bytes for fp32 and bf16 rows
+      if (TMA_ST) {
+        if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free again
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        gemm_epilogue<GC, EPI, true>(stage, bias, &acc_full[buf], par, tmem_acc, m0, nh, g, 0, shape, ep, warp,
+                                     lane TRACE_ARGS);
+      } else {
+        constexpr int CW = GC / 2;  // fp32 rows: two 32-column passes through the same 16 KB
 #pragma unroll 1
-      for (int c = 0; c < GC; c += CW)
-        gemm_epilogue<CW, EPI>(stage, bias + c, &acc_full[buf], par, tmem_acc + c, m0, nh + c, g, 0, shape, ep, warp,
-                               lane TRACE_ARGS);
+        for (int c = 0; c < GC; c += CW)
+          gemm_epilogue<CW, EPI>(stage, bias + c, &acc_full[buf], par, tmem_acc + c, m0, nh + c, g, 0, shape, ep, warp,
+                                 lane TRACE_ARGS);
+      }
       // this warp's TMEM reads of the tile are complete (the epilogue ends its stage 1 with a tcgen05 fence)
       if (lane == 0)
         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty + buf * 8) : "memory");
+      if (TMA_ST) {
+        fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (store_thread) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tma_out)),
+                       "r"(smem_u32(stage)), "r"(nh), "r"(m0), "r"(g)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       if (threadIdx.x == 64 && it < 4) TRACE_PT(0x106);
     }
+    if (TMA_ST && store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes complete before exit
   }
 
   tc_fence_before();

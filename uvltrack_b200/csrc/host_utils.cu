@@ -121,7 +121,7 @@ static int g_gemm_2sm_stages = [] {
 }();
 
 static bool use_2sm(int M, int N, int K, int groups, int splits) {
-  if (!g_gemm_2sm || N % GEMM2_BN || splits != 1) return false;
+  if (!g_gemm_2sm || N % GEMM2_BN || splits != 1 || groups != 1) return false;
   if (g_gemm_2sm >= 2) return true;
   if (M < 4096) return false;
   const long long m_pairs = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
@@ -194,8 +194,8 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   }
   g->two_sm = false;
   if (bn == 512 || (bn == 0 && use_2sm(M, N, K, groups, splits))) {
-    if (N % GEMM2_BN || splits != 1) {
-      set_error("gemm: the CTA-pair kernel needs N % 256 == 0 and no split-K");
+    if (N % GEMM2_BN || splits != 1 || groups != 1) {
+      set_error("gemm: the CTA-pair kernel needs N % 256 == 0, one group and no split-K");
       return 1;
     }
     g->two_sm = true;
@@ -241,6 +241,11 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
   // pairs of CTAs along N share the A tile through TMA multicast (64-row halves) whenever the N tiles pair up
   g->multicast = !g->two_sm && g_gemm_multicast && ((N / bn) % 2 == 0);
   if (g->multicast && make_tma_bf16_3d(&g->tma_a_half, A, K, M, groups, a_ld * 2, a_gstride * 2, GEMM_BM / 2)) return 1;
+  // the CTA-pair kernel stores its bf16 output tiles with TMA (128 x 64 boxes of the [M, out_ld] matrix)
+  g->tma_out = g->tma_a;
+  if (g->two_sm && !ep.out_f32 &&
+      make_tma_bf16_3d(&g->tma_out, ep.out, N, M, 1, ep.out_ld * 2, static_cast<uint64_t>(M) * ep.out_ld * 2, GEMM_BM))
+    return 1;
   // the CTA-pair kernel stages one 128-row half of the 256-wide W tile per CTA
   if (make_tma_bf16_3d(&g->tma_w, W, K, N, groups, w_ld * 2, w_gstride * 2, g->two_sm ? GEMM2_BN / 2 : bn)) return 1;
   return 0;
@@ -271,7 +276,7 @@ static void gemm_launch_2sm(const GemmLaunch& g, cudaStream_t stream) {
   const dim3 grid(2 * clusters), block(GEMM2_THREADS);
 #define UVLT_GEMM2_LAUNCH(EPI)                                                                                  \
   (void)launch_kc(gemm_bf16_tn_2sm_kernel<EPI>, grid, block, gemm2_smem_bytes(g.shape.stages), stream, 2, g.tma_a, \
-                  g.tma_w, g.shape, g.ep)
+                  g.tma_w, g.tma_out, g.shape, g.ep)
   if (g.ep.out_f32) UVLT_GEMM2_LAUNCH(EPI_F32);
   else if (g.ep.act == ACT_GELU) UVLT_GEMM2_LAUNCH(EPI_BF16_GELU);
   else if (g.ep.act == ACT_RELU) UVLT_GEMM2_LAUNCH(EPI_BF16_RELU);

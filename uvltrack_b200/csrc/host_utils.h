@@ -33,6 +33,7 @@ int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
 struct GemmLaunch {
   CUtensorMap tma_a, tma_w;
   CUtensorMap tma_a_half;  // 64-row boxes of A for the multicast variant
+  CUtensorMap tma_out;     // bf16 output matrix, 128 x 64 boxes (CTA-pair kernel: TMA bulk stores)
   bool multicast;
   bool two_sm;  // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 pair tile); bn == 256
   GemmShape shape;
