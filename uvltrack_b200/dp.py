@@ -38,7 +38,8 @@ def init_process_group(backend: str | None = None):
         torch.cuda.set_device(local)
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}  # bind the communicator to the GPU
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
 
