@@ -195,3 +195,27 @@ def test_error_paths(case):
         model.engine.forward_test(T(inp["template"]), T(inp["search"]),
                                   NestedTensor(T(inp["ids"][:, :30]), T(inp["text_mask"][:, :30])), T(inp["prompt"]),
                                   T(inp["flag"]))
+
+
+def test_batch_independence_across_gemm_kernels():
+    """Batch 8 at 256/256 runs fc1 / fc2 / proj through the persistent CTA-pair GEMM (M = 4424 >= 4096) while a
+    sequence run alone on the same engine uses the one-tile-per-CTA kernels.  Both accumulate every output element over
+    K in the same order (k-blocks of 64 in sequence, fp32 in TMEM), so a sequence inside the batch must equal the same
+    sequence alone bit for bit; and the batch must agree with the oracle-pinned small-batch path at all."""
+    from uvltrack_b200.weights import ModelDims
+
+    dims = ModelDims.base(256, 256)
+    cfg = config.baseline_cfg("base", 256, 256)
+    model = registry.MODELS["uvltrack"](cfg, max_batch=8)
+    model.load_state_dict(synthetic_state_dict(dims, seed=0))
+    inp = synthetic_inputs(dims, 8, "MIXED", seed=11)
+    text = NestedTensor(T(inp["ids"]), T(inp["text_mask"]))
+    full = model.engine.forward_test(T(inp["template"]), T(inp["search"]), text, T(inp["prompt"]), T(inp["flag"]))
+    assert all(torch.isfinite(full[k]).all() for k in ("cls_score_test", "bbox_map", "tokens"))
+    for b in (0, 5, 7):
+        one = model.engine.forward_test(T(inp["template"][b:b + 1]), T(inp["search"][b:b + 1]),
+                                        NestedTensor(T(inp["ids"][b:b + 1]), T(inp["text_mask"][b:b + 1])),
+                                        T(inp["prompt"][b:b + 1]), T(inp["flag"][b:b + 1]))
+        for k in ("cls_score_test", "bbox_map", "cont_score", "tokens"):
+            assert torch.equal(one[k][0], full[k][b]), (b, k, float((one[k][0] - full[k][b]).abs().max()))
+    model.engine.close()

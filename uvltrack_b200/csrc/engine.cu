@@ -446,7 +446,8 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
     if (gemm_prepare(&lp.fc2, e->hid, Hd, 0, w.fc2_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 64 : e->force_bn,
                      ep_stream(e, w.fc2_b, rows, 0), sk))
       return nullptr;
-    if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0))
+    if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0,
+                     e->Bm))
       return nullptr;
   }
   if (!skip_text) {
@@ -464,7 +465,7 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
                        ep_stream(e, w.out_b, T, Nv), sk))
         return nullptr;
     }
-    if (attn_prepare(&p->bert_attn, e->t_qkv, B, T, e->H, e->bias_bert, e->t_att, nullptr, 0)) return nullptr;
+    if (attn_prepare(&p->bert_attn, e->t_qkv, B, T, e->H, e->bias_bert, e->t_att, nullptr, 0, e->Bm)) return nullptr;
   }
   {
     const int C = e->C, M = B * e->SS;

@@ -311,7 +311,7 @@ int gemm_launch(const GemmLaunch& g, cudaStream_t stream) {
 }
 
 int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
-                 int n_pad) {
+                 int n_pad, int capacity_batch) {
   (void)n_pad;
   if (vt) {
     set_error("attention: the separate V^T operand of the bring-up kernel is no longer supported (pass NULL)");
@@ -331,15 +331,15 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   a->p.bias = bias;
   a->p.out = reinterpret_cast<__nv_bfloat16*>(out);
   a->B = B;
+  // small grids (every CTA has an SM to itself): two CTAs per query tile, half of the key blocks each
+  const int cb = capacity_batch > 0 ? capacity_batch : B;
+  a->split = g_attn_split && cb * H * ((n + ATT_BQ - 1) / ATT_BQ) <= g_num_sms && (n + ATT_BKV - 1) / ATT_BKV >= 2;
   return 0;
 }
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
-  // small grids (every CTA has an SM to itself): two CTAs per query tile, half of the key blocks each
-  const bool split = g_attn_split && static_cast<int>(grid.x * grid.y * grid.z) <= g_num_sms &&
-                     (a.p.n + ATT_BKV - 1) / ATT_BKV >= 2;
-  if (split) {
+  if (a.split) {
     grid.x *= 2;
     (void)launch_kc(attention_kernel<true>, grid, dim3(ATT_THREADS), AttnSmem::TOTAL_SPLIT, stream, 2, a.tma_qkv, a.tma_kv,
                     a.p);

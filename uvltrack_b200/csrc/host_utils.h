@@ -60,9 +60,12 @@ struct AttnLaunch {
   CUtensorMap tma_kv;   // 64-row boxes (K / V tiles)
   AttnParams p;
   int B;
+  bool split;  // key-split cluster variant (two CTAs per query tile)
 };
+// capacity_batch: the batch size the split decision is made for (the engine passes its max_batch, so that a sequence's
+// result does not depend on how many sequences share the call; 0 = use B)
 int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
-                 int n_pad);
+                 int n_pad, int capacity_batch = 0);
 int attn_launch(const AttnLaunch& a, cudaStream_t stream);
 
 int init_kernel_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation; idempotent
