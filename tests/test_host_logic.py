@@ -130,3 +130,38 @@ def test_opencv_linear_resize_fixed_point_model():
         src = rng.integers(0, 256, (sz, sz, 3), dtype=np.uint8)
         for out in (128, 256):
             assert np.array_equal(resize(src, out), cv2.resize(src, (out, out))), (sz, out)
+
+
+def test_search_window_contains_every_pixel_sample_target_reads():
+    """BatchTracker.track() uploads only pp.search_window() of each frame.  Property: blanking everything OUTSIDE the
+    window never changes the crop (boxes inside, over the border, outside the frame, tiny and huge)."""
+    rng = np.random.default_rng(3)
+    H, W = 120, 160
+    frame = rng.integers(1, 256, size=(H, W, 3), dtype=np.uint8)  # no zeros: padding is distinguishable
+    n_none = 0
+    for i in range(400):
+        w, h = rng.uniform(1.0, 90.0), rng.uniform(1.0, 90.0)
+        x, y = rng.uniform(-80.0, W + 40.0), rng.uniform(-80.0, H + 40.0)
+        if i % 7 == 0:  # exact .5 origins: Python's round() is half-to-even
+            x, y, w, h = float(int(x)) + 0.5, float(int(y)), float(int(w) + 1), float(int(h) + 1)
+        factor = [2.0, 4.0, 5.0][i % 3]
+        box = [x, y, w, h]
+        side = int(np.ceil(np.sqrt(w * h) * factor))
+        x1, y1 = int(round(x + 0.5 * w - side * 0.5)), int(round(y + 0.5 * h - side * 0.5))
+        win = pp.search_window(box, factor, H, W)
+        if x1 + side <= 0 or y1 + side <= 0 or x1 >= W - 1 or y1 >= H - 1:
+            # Window entirely outside the frame.  The reference's own slicing is not meaningful here (a negative stop
+            # index wraps around, an empty slice reaches copyMakeBorder); clip_box(margin=10) keeps every tracked box
+            # >= 10 px inside the frame, so Tracker.track() never gets here.  The window must simply be empty or tiny.
+            n_none += win is None
+            continue
+        full, rf, _ = pp.sample_target(frame, box, factor, 64)
+        assert win is not None, (i, box)
+        xa, ya, xb, yb = win
+        assert 0 <= xa < xb <= W and 0 <= ya < yb <= H
+        masked = np.zeros_like(frame)
+        masked[ya:yb, xa:xb] = frame[ya:yb, xa:xb]
+        part, rf2, _ = pp.sample_target(masked, box, factor, 64)
+        assert rf == rf2 and np.array_equal(full, part), (i, box, win)
+    assert n_none > 0
+    assert pp.search_window([10.0, 10.0, 0.0, 5.0], 4.0, H, W) is None   # degenerate box: "Too small bounding box."

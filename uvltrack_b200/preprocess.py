@@ -37,6 +37,24 @@ def sample_target(im: np.ndarray, target_bb, search_area_factor: float, output_s
     return resized, resize_factor, bbox
 
 
+def search_window(target_bb, search_area_factor: float, frame_h: int, frame_w: int, slack: int = 2):
+    """Rectangle [xa, xb) x [ya, yb) of the frame that contains every pixel ``sample_target`` reads for this box
+    (the crop window x1..x2, y1..y2 of processing_utils.py:183-199 clipped to the frame), padded by `slack` pixels
+    against the rounding of the window origin.  None when the window lies entirely outside the frame (the crop is all
+    padding) or the box is degenerate.  Used by BatchTracker.track() to upload only this part of each frame."""
+    x, y, w, h = [float(v) for v in target_bb]
+    side = math.ceil(math.sqrt(max(w * h, 0.0)) * search_area_factor)
+    if side < 1:
+        return None
+    xa = max(int(math.floor(x + 0.5 * w - 0.5 * side)) - slack, 0)
+    ya = max(int(math.floor(y + 0.5 * h - 0.5 * side)) - slack, 0)
+    xb = min(int(math.floor(x + 0.5 * w - 0.5 * side)) + side + slack + 2, frame_w)
+    yb = min(int(math.floor(y + 0.5 * h - 0.5 * side)) + side + slack + 2, frame_h)
+    if xb <= xa or yb <= ya:
+        return None
+    return xa, ya, xb, yb
+
+
 def grounding_resize(im: np.ndarray, output_sz: int):
     """Aspect-preserving resize of the whole frame to fit output_sz, centre padded with zeros
     (lib/train/data/processing_utils.py:60-141, image part only)."""

@@ -283,14 +283,10 @@ class BatchTracker:
             def stage(b):
                 # only the search window of the frame is read by sample_target (processing_utils.py:183-199): stage and
                 # upload that rectangle (+2 px of slack for the rounding of the window origin), not the whole frame
-                x, y, w, hh = self.state[b]
-                side = math.ceil(math.sqrt(max(w * hh, 0.0)) * factor)
-                xa = max(int(math.floor(x + 0.5 * w - 0.5 * side)) - 2, 0)
-                ya = max(int(math.floor(y + 0.5 * hh - 0.5 * side)) - 2, 0)
-                xb = min(xa + side + 6, W)
-                yb = min(ya + side + 6, H)
-                if xb <= xa or yb <= ya:
-                    return 0  # window entirely outside the frame: the crop is all padding
+                win = pp.search_window(self.state[b], factor, H, W)
+                if win is None:
+                    return 0  # window entirely outside the frame (the crop is all padding) or a degenerate box
+                xa, ya, xb, yb = win
                 np.copyto(self.frames_np[b, ya:yb, xa:xb], images[b][ya:yb, xa:xb])
                 off = b * per + ya * pitch + xa * 3
                 if lib.uvlt_upload_frames_2d(h, f["frames_ptr"] + off, pitch, off, pitch, (xb - xa) * 3, yb - ya,
