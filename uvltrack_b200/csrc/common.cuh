@@ -60,10 +60,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
   p = fmaf(t, p, 0.254829592f);
-  // gelu(x) = x * Phi(x) = max(x, 0) - |x| * (erfc(|x| / sqrt 2) / 2): one FMNMX + one FFMA instead of a compare / select /
-  // subtract / multiply (the 0.5 is folded into the product)
-  const float half_erfc = (0.5f * p) * (t * e);
-  return fmaf(-fabsf(x), half_erfc, fmaxf(x, 0.0f));
+  const float half_erfc = 0.5f * p * t * e;
+  return x * (x > 0.0f ? 1.0f - half_erfc : half_erfc);
 }
 
 // ----------------------------------------------------------------------------------------------
