@@ -202,6 +202,13 @@ UVLT_API int uvlt_last_launch_count(uvlt_handle h);
  * Operator-level entry points (device pointers; used by the per-operator parity tests)
  * ---------------------------------------------------------------------------------------------------------- */
 
+/* Host-only query (no GPU touched): which kernel configuration the library picks for a [groups][M,K] x [N,K]^T GEMM.
+ * split_k != 0: the caller can consume split-K partials (fp32 output summed by the next LayerNorm, i.e. fc2).
+ * plan[0] = 1 when the persistent CTA-pair kernel (tcgen05 cta_group::2) runs it, plan[1] = tile width BN,
+ * plan[2] = split-K factor, plan[3] = split-K factor if this were the box head's first conv GEMM.  The rules encode
+ * B200 measurements (profiles/r01_gemm_2sm.md, tools/kernel_sweep.py); tests/test_host_logic.py pins them. */
+UVLT_API int uvlt_gemm_plan(int M, int N, int K, int groups, int out_f32, int act, int split_k, int32_t* plan);
+
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + resid;  A, W bf16 row-major; bias fp32 [N] or NULL; resid fp32 [M,N]
  * or NULL (may alias out when out_f32); out bf16 or fp32.  nn.Linear semantics (block.py:49,59; utils.py:63-69).
  * bn: tile width 32/64/128/256, 0 = auto, 512 = the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tile per pair of

@@ -165,3 +165,37 @@ def test_search_window_contains_every_pixel_sample_target_reads():
         assert rf == rf2 and np.array_equal(full, part), (i, box, win)
     assert n_none > 0
     assert pp.search_window([10.0, 10.0, 0.0, 5.0], 4.0, H, W) is None   # degenerate box: "Too small bounding box."
+
+
+def test_gemm_planner_rules_are_pinned():
+    """uvlt_gemm_plan (host only): the kernel-selection rules encode B200 measurements (profiles/r01_gemm_2sm.md,
+    DESIGN.md section 4); pin them for the benchmark shapes so that a change of rule is a conscious one."""
+    import ctypes as C
+
+    from uvltrack_b200 import _cabi
+
+    lib = _cabi.load()
+
+    def plan(M, N, K, f32=0, act=0, split_k=0, groups=1):
+        p = (C.c_int32 * 4)()
+        assert lib.uvlt_gemm_plan(M, N, K, groups, f32, act, split_k, p) == 0
+        return list(p)[:3]   # [CTA-pair kernel, tile width, split-K]
+
+    n = 513  # tokens per sequence at 256/256, BBOX
+    # batch 1: narrow tiles for parallelism, fc2 cut six ways, head conv 0 nine ways
+    assert plan(n, 2304, 768) == [0, 64, 1] and plan(n, 768, 768, 1) == [0, 32, 1]
+    assert plan(n, 3072, 768, 0, 1) == [0, 64, 1] and plan(n, 768, 3072, 1, 0, 1) == [0, 64, 6]
+    p = (C.c_int32 * 4)()
+    for B, hs in ((1, 9), (2, 4), (4, 2), (8, 1)):
+        assert lib.uvlt_gemm_plan(B * 256, 1024, 6912, 1, 0, 2, 0, p) == 0 and p[3] == hs
+    # split-K fades out as the grid fills; never combined with the CTA-pair kernel
+    assert [plan(B * n, 768, 3072, 1, 0, 1)[2] for B in (1, 2, 4, 8, 32)] == [6, 4, 2, 1, 1]
+    # batch 32: every layer GEMM on the persistent CTA-pair kernel
+    for N, K, f32, act in ((2304, 768, 0, 0), (768, 768, 1, 0), (3072, 768, 0, 1), (768, 3072, 1, 0)):
+        assert plan(32 * n, N, K, f32, act, int(K > 2048)) == [1, 256, 1]
+    # batch 16: proj would leave most clusters idle in its second round of tiles -> one-CTA 128-wide tiles
+    assert plan(16 * n, 768, 768, 1) == [0, 128, 1] and plan(16 * n, 3072, 768, 0, 1) == [1, 256, 1]
+    # below M = 4096, grouped GEMMs and N % 256 != 0 never use the pair kernel
+    assert plan(4 * n, 2304, 768)[0] == 0 and plan(32 * 256, 128, 2304, 0, 2, 0, groups=4)[0] == 0
+    assert plan(32 * n, 320, 768)[0] == 0
+    assert lib.uvlt_gemm_plan(0, 8, 8, 1, 0, 0, 0, p) != 0

@@ -69,6 +69,7 @@ SIGNATURES = {
     "uvlt_upload_frames_2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "uvlt_gemm_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_int32)]),
     "uvlt_op_gemm_splitk": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, C.POINTER(c_int), _P]),
     "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,
                                      c_int, _P]),

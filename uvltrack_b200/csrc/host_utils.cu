@@ -120,7 +120,7 @@ static int g_gemm_2sm_stages = [] {
   return e ? std::min(std::max(std::atoi(e), 2), GEMM2_MAX_STAGES) : GEMM2_MAX_STAGES;
 }();
 
-static bool use_2sm(int M, int N, int K, int groups, int splits) {
+bool use_2sm(int M, int N, int K, int groups, int splits) {
   if (!g_gemm_2sm || N % GEMM2_BN || splits != 1 || groups != 1) return false;
   if (g_gemm_2sm >= 2) return true;
   if (M < 4096) return false;

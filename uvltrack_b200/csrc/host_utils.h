@@ -53,6 +53,8 @@ int pick_splits(int M, int N, int K);
 int pick_head_splits(int M, int N, int K);
 int gemm_launch(const GemmLaunch& g, cudaStream_t stream);
 int pick_bn(int M, int N, int groups, bool out_f32, int act);
+// true: the persistent CTA-pair kernel takes this GEMM (rule and measurements in host_utils.cu)
+bool use_2sm(int M, int N, int K, int groups, int splits);
 extern int g_gemm_multicast;  // UVLT_MULTICAST=0 disables the cluster / TMA-multicast GEMM variant
 
 struct AttnLaunch {

@@ -55,6 +55,17 @@ int uvlt_op_gemm_splitk(const void* A, const void* W, const float* bias, const f
   return 0;
 }
 
+int uvlt_gemm_plan(int M, int N, int K, int groups, int out_f32, int act, int split_k, int32_t* plan) {
+  if (!plan || M <= 0 || N <= 0 || K <= 0 || groups <= 0) return 1;
+  const int splits = split_k ? pick_splits(M, N, K) : 1;
+  const bool two = use_2sm(M, N, K, groups, splits);
+  plan[0] = two ? 1 : 0;
+  plan[1] = two ? 256 : (splits > 1 ? 64 : pick_bn(M, N, groups, out_f32 != 0, act));
+  plan[2] = splits;
+  plan[3] = pick_head_splits(M, N, K);
+  return 0;
+}
+
 int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,
                          int act, long long out_ld, long long out_gstride, int bn, void* stream) {
   if (init_kernel_attributes()) return 1;
