@@ -451,7 +451,7 @@ def run_b200(a):
         "step_model": {"gemm_gflop_per_frame": round(g_fl / 1e9, 2), "attention_gflop_per_frame": round(a_fl / 1e9, 2),
                        "achieved_tflops_whole_step": round((g_fl + a_fl) * B / (dev_s / a.steps) / 1e12, 2)},
     }
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only (the other arms: --impl reference)
         frames = a.cpu_frames or (60 if a.arch == "base" else 16)
         fps, dt, impl, threads = cpu_frames_per_second(dims, a.mode, frames, 1)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": threads, "kind": "port",
