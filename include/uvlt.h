@@ -195,6 +195,21 @@ UVLT_API int uvlt_op_crop_resize(const uint8_t* frames, int32_t frame_h, int32_t
                                  double factor, int32_t out_size, uint8_t* crops, double* resize_factor, int32_t batch,
                                  void* stream);
 
+/* The state update of Tracker.track alone (lib/test/tracker/uvltrack.py:123-125: pred_box * search_size / resize_factor in
+ * fp32, map_box_back :167-173 and clip_box(margin 10) lib/utils/box_ops.py:117-126 in fp64), device pointers:
+ * net_boxes fp32 [B,4] (cx, cy, w, h of the network), resize_factor fp64 [B], state fp64 [B,4] updated in place. */
+UVLT_API int uvlt_op_box_update(const float* net_boxes, const double* resize_factor, int32_t search_size, int32_t frame_h,
+                                int32_t frame_w, double* state, int32_t batch, void* stream);
+
+/* Tracker.anno2mask (lib/test/tracker/uvltrack.py:183-194): boxes fp32 [B,4] normalised (x, y, w, h) inside the crop ->
+ * mask uint8 [B, size*size] (1 = cell centre inside the box, plus the cell under the box centre).  Device pointers. */
+UVLT_API int uvlt_op_anno2mask(const float* boxes, int32_t size, uint8_t* mask, int32_t batch, void* stream);
+
+/* Preprocessor_wo_mask.process (lib/test/tracker/tracker_utils.py:25-29): crops uint8 [B,S,S,3] -> out fp32 [B,3,S,S],
+ * ((x / 255) - mean) / std.  Device pointers.  (Search crops never take this path: their normalisation is fused into the
+ * patch embedding; this is for the template / context crops of Tracker.initialize.) */
+UVLT_API int uvlt_op_normalize_u8(const uint8_t* crops, float* out, int32_t size, int32_t batch, void* stream);
+
 /* number of kernels the last forward/track call launched (for bench.py's gpu_launches) */
 UVLT_API int uvlt_last_launch_count(uvlt_handle h);
 

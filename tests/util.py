@@ -28,7 +28,7 @@ def max_abs(a, b):
 
 
 def golden_cases(include_large=True):
-    names = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    names = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(("base_", "large_")))
     return [n for n in names if include_large or not n.startswith("large")]
 
 

@@ -198,6 +198,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same bound, no printf: a device-side printf is an ABI call, which ptxas cannot place in code that runs under a
+// setmaxnreg register budget (attention2.cuh).
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // proxies / fences
 // ----------------------------------------------------------------------------------------------

@@ -60,6 +60,17 @@ static int g_attn_split = [] {
   return (e && e[0] == '0') ? 0 : 1;
 }();
 
+// UVLT_ATTN_V=1 selects the first-generation attention kernel (attention.cuh) for A/B timing; default: attention2.cuh.
+// UVLT_ATTN_POLY=0 keeps every exponential on the MUFU.
+static int g_attn_v = [] {
+  const char* e = getenv("UVLT_ATTN_V");
+  return (e && e[0] == '1') ? 1 : 2;
+}();
+static int g_attn_poly = [] {
+  const char* e = getenv("UVLT_ATTN_POLY");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+
 int init_kernel_attributes() {
   static int status = -1;
   static std::mutex mu;
@@ -87,6 +98,8 @@ int init_kernel_attributes() {
                                     AttnSmem::TOTAL_SPLIT));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
   {
     int dev = 0, sms = 0;
     UVLT_CUDA_OK(cudaGetDevice(&dev));
@@ -334,10 +347,28 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   // small grids (every CTA has an SM to itself): two CTAs per query tile, half of the key blocks each
   const int cb = capacity_batch > 0 ? capacity_batch : B;
   a->split = g_attn_split && cb * H * ((n + ATT_BQ - 1) / ATT_BQ) <= g_num_sms && (n + ATT_BKV - 1) / ATT_BKV >= 2;
+  a->v2 = g_attn_v == 2;
+  a->poly = g_attn_poly != 0;
+  a->p2.n = n;
+  a->p2.H = H;
+  a->p2.scale_log2 = a->p.scale_log2;
+  a->p2.bias = bias;
+  a->p2.out = a->p.out;
+  // small grids (decided from the engine's capacity, so that a sequence's result does not depend on the batch it shares
+  // a call with): one query tile per CTA, the two slots split its key blocks
+  a->p2.split_all = (g_attn_split && cb * H * ((n + AT2_BQ - 1) / AT2_BQ) <= g_num_sms) ? 1 : 0;
   return 0;
 }
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
+  if (a.v2) {
+    const int ntiles = (a.p2.n + AT2_BQ - 1) / AT2_BQ;
+    dim3 grid2(a.p2.split_all ? ntiles : (ntiles + 1) / 2, a.p2.H, a.B);
+    if (a.poly) UVLT_LAUNCH(attention2_kernel<true>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.p2);
+    else UVLT_LAUNCH(attention2_kernel<false>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.p2);
+    UVLT_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
   if (a.split) {
     grid.x *= 2;

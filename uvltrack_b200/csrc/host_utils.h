@@ -8,6 +8,7 @@
 #include <string>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "gemm.cuh"
 
 namespace uvlt {
@@ -63,6 +64,10 @@ struct AttnLaunch {
   AttnParams p;
   int B;
   bool split;  // key-split cluster variant (two CTAs per query tile)
+  // second-generation kernel (attention2.cuh): two query tiles (or two key halves of one tile) per CTA, P in TMEM
+  bool v2;
+  bool poly;   // a quarter of the exponentials on the FMA pipe
+  Attn2Params p2;
 };
 // capacity_batch: the batch size the split decision is made for (the engine passes its max_batch, so that a sequence's
 // result does not depend on how many sequences share the call; 0 = use B)

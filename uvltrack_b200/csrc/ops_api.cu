@@ -134,4 +134,29 @@ int uvlt_op_build_bias(const long long* flag, const float* text_mask, int B, int
   return 0;
 }
 
+int uvlt_op_box_update(const float* net_boxes, const double* resize_factor, int32_t search_size, int32_t frame_h,
+                       int32_t frame_w, double* state, int32_t B, void* stream) {
+  if (!net_boxes || !resize_factor || !state || B < 1 || search_size < 1) { set_error("uvlt_op_box_update: bad argument"); return 1; }
+  UVLT_LAUNCH(box_update_kernel, dim3((B + 63) / 64), dim3(64), 0, static_cast<cudaStream_t>(stream), net_boxes,
+              resize_factor, search_size, frame_h, frame_w, state, B);
+  if (cudaGetLastError() != cudaSuccess) { set_error("box_update launch failed"); return 1; }
+  return 0;
+}
+
+int uvlt_op_anno2mask(const float* boxes, int32_t size, uint8_t* mask, int32_t B, void* stream) {
+  if (!boxes || !mask || B < 1 || size < 1) { set_error("uvlt_op_anno2mask: bad argument"); return 1; }
+  UVLT_LAUNCH(anno2mask_kernel, dim3((size * size + 127) / 128, B), dim3(128), 0, static_cast<cudaStream_t>(stream), boxes,
+              size, mask, B);
+  if (cudaGetLastError() != cudaSuccess) { set_error("anno2mask launch failed"); return 1; }
+  return 0;
+}
+
+int uvlt_op_normalize_u8(const uint8_t* crops, float* out, int32_t size, int32_t B, void* stream) {
+  if (!crops || !out || B < 1 || size < 1) { set_error("uvlt_op_normalize_u8: bad argument"); return 1; }
+  UVLT_LAUNCH(normalize_u8_kernel, dim3((size * size + 255) / 256, B), dim3(256), 0, static_cast<cudaStream_t>(stream),
+              crops, out, size, B);
+  if (cudaGetLastError() != cudaSuccess) { set_error("normalize_u8 launch failed"); return 1; }
+  return 0;
+}
+
 }  // extern "C"

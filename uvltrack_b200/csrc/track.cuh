@@ -120,4 +120,56 @@ __device__ __forceinline__ void box_update(const float4 net, double rf, int sear
   st[3] = fmax(margin, __dadd_rn(y2, -y1));
 }
 
+// box_update alone, one thread per sequence (operator-level entry for the parity fixtures of tests/golden/preproc.npz)
+static __global__ void box_update_kernel(const float* net, const double* rf, int search_size, int H, int W, double* state,
+                                         int B) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float4 bb = make_float4(net[4 * b], net[4 * b + 1], net[4 * b + 2], net[4 * b + 3]);
+  box_update(bb, rf[b], search_size, H, W, state + 4 * b);
+}
+
+// Tracker.anno2mask (lib/test/tracker/uvltrack.py:183-194): normalised [x, y, w, h] boxes -> cells of a size x size grid
+// whose centre lies strictly inside the box, plus the cell under the box centre.  fp32 arithmetic in the reference's
+// order (box_xywh_to_xyxy then * size; torch's .long() truncates toward zero), so the mask is bit-identical.
+static __global__ void anno2mask_kernel(const float* boxes, int size, uint8_t* mask, int B) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || cell >= size * size) return;
+  const float fs = static_cast<float>(size);
+  const float x1 = __fmul_rn(boxes[4 * b], fs), y1 = __fmul_rn(boxes[4 * b + 1], fs);
+  const float x2 = __fmul_rn(__fadd_rn(boxes[4 * b], boxes[4 * b + 2]), fs);
+  const float y2 = __fmul_rn(__fadd_rn(boxes[4 * b + 1], boxes[4 * b + 3]), fs);
+  const int r = cell / size, c = cell - r * size;
+  const float cx = static_cast<float>(c) + 0.5f, cy = static_cast<float>(r) + 0.5f;
+  bool in = (cx > x1) && (cx < x2) && (cy > y1) && (cy < y2);
+  const long long ccx = static_cast<long long>(__fdiv_rn(__fadd_rn(x1, x2), 2.0f));
+  const long long ccy = static_cast<long long>(__fdiv_rn(__fadd_rn(y1, y2), 2.0f));
+  // the reference indexes mask[b, cy, cx] with Python semantics: a negative index wraps once, anything else out of range
+  // raises; in-range indices are the only ones a box inside its crop produces
+  const long long wx = ccx < 0 ? ccx + size : ccx, wy = ccy < 0 ? ccy + size : ccy;
+  in = in || (wx == c && wy == r);
+  mask[static_cast<long long>(b) * size * size + cell] = in ? 1 : 0;
+}
+
+// Preprocessor_wo_mask.process (lib/test/tracker/tracker_utils.py:25-29): uint8 HWC crop -> fp32 [3, S, S],
+// ((x / 255) - mean) / std in fp32 in that order.
+static __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* crops, float* out, int S, int B) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || pix >= S * S) return;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  const uint8_t* src = crops + (static_cast<long long>(b) * S * S + pix) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    out[(static_cast<long long>(b) * 3 + c) * S * S + pix] =
+        __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(src[c]), 255.0f), mean[c]), stdv[c]);
+}
+
 }  // namespace uvlt

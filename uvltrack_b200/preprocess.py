@@ -75,6 +75,19 @@ def grounding_resize(im: np.ndarray, output_sz: int):
     return cv2.copyMakeBorder(img, y1, y2, x1, x2, cv2.BORDER_CONSTANT, value=(0, 0, 0))
 
 
+def grounding_box(pred_cxcywh, frame_h: int, frame_w: int):
+    """The box arithmetic of Tracker.grounding (lib/test/tracker/uvltrack.py:58-62): the network's normalised
+    (cx, cy, w, h) of the padded square frame -> [x, y, w, h] in frame pixels.  fp32 tensor arithmetic
+    (`pred * max(h, w)`, box_cxcywh_to_xywh), then Python floats; the padding offset of the shorter side is removed."""
+    p = np.asarray(pred_cxcywh, dtype=np.float32).reshape(4) * np.float32(max(frame_h, frame_w))
+    half = np.float32(0.5)
+    box = [float(np.float32(p[0] - half * p[2])), float(np.float32(p[1] - half * p[3])), float(p[2]), float(p[3])]
+    dx, dy = min(0, (frame_w - frame_h) / 2), min(0, (frame_h - frame_w) / 2)
+    box[0] = box[0] + dx
+    box[1] = box[1] + dy
+    return box
+
+
 def normalize_image(img_u8: np.ndarray) -> np.ndarray:
     """Preprocessor_wo_mask.process (lib/test/tracker/tracker_utils.py:25-29) on the host: HWC uint8 -> [1,3,H,W] fp32."""
     mean = np.array([0.485, 0.456, 0.406], dtype=np.float32).reshape(1, 3, 1, 1)

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 import os
+import unicodedata
 
 import numpy as np
 
@@ -22,10 +23,37 @@ from .misc import NestedTensor
 from .model import build_model
 
 
+def _is_whitespace(ch: str) -> bool:
+    return ch in " \t\n\r" or unicodedata.category(ch) == "Zs"
+
+
+def _is_control(ch: str) -> bool:
+    if ch in "\t\n\r":
+        return False
+    return unicodedata.category(ch).startswith("C")
+
+
+def _is_punctuation(ch: str) -> bool:
+    cp = ord(ch)
+    # every non-alphanumeric ASCII character counts as punctuation ("^", "$", "`" included), as in BERT
+    if 33 <= cp <= 47 or 58 <= cp <= 64 or 91 <= cp <= 96 or 123 <= cp <= 126:
+        return True
+    return unicodedata.category(ch).startswith("P")
+
+
+def _is_cjk(cp: int) -> bool:
+    return (0x4E00 <= cp <= 0x9FFF or 0x3400 <= cp <= 0x4DBF or 0x20000 <= cp <= 0x2A6DF or 0x2A700 <= cp <= 0x2B73F or
+            0x2B740 <= cp <= 0x2B81F or 0x2B820 <= cp <= 0x2CEAF or 0xF900 <= cp <= 0xFAFF or 0x2F800 <= cp <= 0x2FA1F)
+
+
 class WordPieceTokenizer:
-    """Minimal BERT uncased tokenizer (what ``BertTokenizer.from_pretrained(vocab, do_lower_case=True)`` of
-    pytorch_pretrained_bert does for plain ASCII queries): lower-case, split on whitespace and punctuation, greedy
-    longest-match-first WordPiece with '##' continuations, '[UNK]' for unmatched words."""
+    """BERT uncased tokenizer: what ``BertTokenizer.from_pretrained(vocab, do_lower_case=True)`` of
+    pytorch_pretrained_bert does (lib/test/tracker/uvltrack.py:39,206): BasicTokenizer (invalid / control characters
+    removed, whitespace normalised, CJK characters isolated, lower-casing, NFD accent stripping, punctuation split) then
+    greedy longest-match-first WordPiece with '##' continuations, '[UNK]' for unmatched or over-long words.  Pinned by
+    tests/golden/tokenizer.json (generated with transformers.BertTokenizer on tests/golden/mini_vocab.txt)."""
+
+    NEVER_SPLIT = ("[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]")
 
     def __init__(self, vocab_path: str):
         self.vocab = {}
@@ -34,24 +62,38 @@ class WordPieceTokenizer:
                 self.vocab[line.rstrip("\n")] = i
         self.unk = "[UNK]"
 
-    @staticmethod
-    def _basic(text: str):
-        out, cur = [], ""
-        for ch in text.lower():
-            if ch.isspace():
-                if cur:
-                    out.append(cur)
-                    cur = ""
-            elif not ch.isalnum():
-                if cur:
-                    out.append(cur)
-                    cur = ""
-                out.append(ch)
+    @classmethod
+    def _basic(cls, text: str):
+        cleaned = []
+        for ch in text:
+            cp = ord(ch)
+            if cp == 0 or cp == 0xFFFD or _is_control(ch):
+                continue
+            if _is_whitespace(ch):
+                cleaned.append(" ")
+            elif _is_cjk(cp):
+                cleaned.extend((" ", ch, " "))
             else:
-                cur += ch
-        if cur:
-            out.append(cur)
-        return out
+                cleaned.append(ch)
+        out = []
+        for tok in "".join(cleaned).split():
+            if tok not in cls.NEVER_SPLIT:
+                tok = "".join(c for c in unicodedata.normalize("NFD", tok.lower()) if unicodedata.category(c) != "Mn")
+            if tok in cls.NEVER_SPLIT:
+                out.append(tok)
+                continue
+            cur = ""
+            for ch in tok:
+                if _is_punctuation(ch):
+                    if cur:
+                        out.append(cur)
+                        cur = ""
+                    out.append(ch)
+                else:
+                    cur += ch
+            if cur:
+                out.append(cur)
+        return " ".join(out).split()
 
     def tokenize(self, text: str):
         toks = []
@@ -77,7 +119,7 @@ class WordPieceTokenizer:
         return toks
 
     def convert_tokens_to_ids(self, tokens):
-        return [self.vocab.get(t, self.vocab.get(self.unk, 100)) for t in tokens]
+        return [self.vocab[t] for t in tokens]  # KeyError for a token outside the vocabulary, like the reference
 
 
 def extract_token_from_nlp(tokenizer, nlp: str, seq_length: int):
@@ -154,8 +196,15 @@ class BatchTracker:
     # ------------------------------------------------------------------------------------------------------
     def _tokens_for(self, info):
         if "text_ids" in info:  # pre-tokenised query (synthetic runs: no vocabulary file is available offline)
-            ids = list(info["text_ids"])
-            mask = list(info.get("text_mask", [1 if i != 0 else 0 for i in ids]))
+            ids = [int(i) for i in info["text_ids"]]
+            mask = [int(m) for m in info.get("text_mask", [1 if i != 0 else 0 for i in ids])]
+            if len(mask) != len(ids):
+                raise ValueError("info['text_mask'] and info['text_ids'] differ in length")
+            if len(ids) > self.max_query_len:
+                # extract_token_from_nlp keeps seq_length - 2 word pieces between [CLS] and [SEP] (tracker :207-208):
+                # cut the middle, keep the trailing [SEP]
+                ids = ids[: self.max_query_len - 1] + ids[-1:]
+                mask = mask[: self.max_query_len - 1] + mask[-1:]
             pad = self.max_query_len - len(ids)
             return ids + [0] * pad, mask + [0] * pad
         if self.tokenizer is None:
@@ -177,11 +226,7 @@ class BatchTracker:
         cm = torch.zeros(1, d.nx, dtype=torch.uint8, device="cuda")
         text = NestedTensor(torch.tensor([ids]).cuda(), torch.tensor([mask]).cuda())
         out = self.network.forward(template, ground, text, tm, cm, torch.tensor([[1]]).cuda())
-        cx, cy, bw, bh = (out["pred_boxes"][0, 0] * float(max(h, w))).tolist()
-        box = [cx - 0.5 * bw, cy - 0.5 * bh, bw, bh]
-        box[0] += min(0, (w - h) / 2)
-        box[1] += min(0, (h - w) / 2)
-        return box
+        return pp.grounding_box(out["pred_boxes"][0, 0].cpu().numpy(), h, w)
 
     def initialize(self, images, infos):
         """lib/test/tracker/uvltrack.py:70-104 for every sequence of the batch."""
