@@ -161,6 +161,21 @@ def test_gemm_cluster_multicast_variant_matches():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("poly", ["0", "1"])
+def test_attention_second_generation_kernel_matches(poly):
+    """attention2.cuh (P in tensor memory, TMEM-operand PV MMA, two slots per CTA; selected with UVLT_ATTN_V=2) must pass
+    the same parity cases as the default kernel, with and without the FMA-pipe exponentials."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, UVLT_ATTN_V="2", UVLT_ATTN_POLY=poly)
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k", "test_attention and not second",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("M,splits", [(513, 4), (513, 0), (1026, 2), (4104, 0)])
 def test_gemm_split_k(M, splits):
     """fc2 at small batch: K is cut in `splits` CTAs per tile; split 0 carries bias + residual, the other splits leave raw

@@ -159,7 +159,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   uint64_t* pv_done = p_full + 1;                // PV_j drained: P buffer reusable, O includes block j
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int q0 = (SPLIT ? (blockIdx.x >> 1) : blockIdx.x) * ATT_BQ;
   const int h = blockIdx.y;
@@ -199,23 +199,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   pdl_wait();  // bias and qkv come from earlier kernels of the chain
   pdl_trigger();
 
+  // producer and MMA warps stay converged, one elected lane issues the asynchronous instructions (elect_one_sync in
+  // common.cuh: no ELECT / R2UR waterfall loop around every tcgen05.mma / TMA instruction)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------- TMA producer ----------------
-      mbar_expect_tx(q_full, AttnSmem::Q_BYTES);
-      tma_load_3d(sQ, &tma_q, q_full, h * ATT_D, q0, b);
+      if (elect_one_sync()) {
+        mbar_expect_tx(q_full, AttnSmem::Q_BYTES);
+        tma_load_3d(sQ, &tma_q, q_full, h * ATT_D, q0, b);
+      }
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;
+#pragma unroll 1
       for (int j = jb; j < je; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * AttnSmem::KV_BYTES);
-        tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
-        tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&kv_full[s], 2 * AttnSmem::KV_BYTES);
+          tma_load_3d(sK + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], D + h * ATT_D, j * ATT_BKV, b);
+          tma_load_3d(sV + s * AttnSmem::KV_BYTES, &tma_kv, &kv_full[s], 2 * D + h * ATT_D, j * ATT_BKV, b);
+        }
+        __syncwarp();
         if (++s == ATT_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issuer ----------------
       const int last_valid = p.n - (nblk - 1) * ATT_BKV;  // keys in the last block
       const uint32_t idesc_full = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0);
@@ -233,11 +242,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       auto issue_qk = [&](int j) {
         const uint64_t kd = kd_base + KV_STEP * sq;
         const uint32_t idesc = (j == nblk - 1) ? idesc_last : idesc_full;
-        umma_bf16_ss(tmem_S, qd, kd, idesc, 0u);
-        umma_bf16_ss(tmem_S, qd + 2, kd + 2, idesc, 1u);
-        umma_bf16_ss(tmem_S, qd + 4, kd + 4, idesc, 1u);
-        umma_bf16_ss(tmem_S, qd + 6, kd + 6, idesc, 1u);
-        umma_commit(s_full);
+        if (elect_one_sync()) {
+          umma_bf16_ss(tmem_S, qd, kd, idesc, 0u);
+          umma_bf16_ss(tmem_S, qd + 2, kd + 2, idesc, 1u);
+          umma_bf16_ss(tmem_S, qd + 4, kd + 4, idesc, 1u);
+          umma_bf16_ss(tmem_S, qd + 6, kd + 6, idesc, 1u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
         if (++sq == ATT_STAGES) { sq = 0; phq ^= 1; }
       };
       mbar_wait(q_full, 0);
@@ -245,6 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       tc_fence_after();
       issue_qk(jb);
       int sv = 0;  // ring stage of the next PV
+#pragma unroll 1
       for (int j = jb; j < je; ++j) {
         const int jj = j - jb;
         if (j + 1 < je) {
@@ -259,12 +272,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         const int ksteps = (j == nblk - 1) ? ((last_valid + 15) >> 4) : (ATT_BKV / 16);
         const uint64_t vd = vd_base + KV_STEP * sv;
         const uint64_t pd = pd_base;
-        umma_bf16_ss(tmem_O, pd, vd, idesc_pv, jj > 0 ? 1u : 0u);
-        if (ksteps > 1) umma_bf16_ss(tmem_O, pd + 2, vd + 128, idesc_pv, 1u);
-        if (ksteps > 2) umma_bf16_ss(tmem_O, pd + 4, vd + 256, idesc_pv, 1u);
-        if (ksteps > 3) umma_bf16_ss(tmem_O, pd + 6, vd + 384, idesc_pv, 1u);
-        umma_commit(&kv_empty[sv]);
-        umma_commit(pv_done);
+        if (elect_one_sync()) {
+          umma_bf16_ss(tmem_O, pd, vd, idesc_pv, jj > 0 ? 1u : 0u);
+          if (ksteps > 1) umma_bf16_ss(tmem_O, pd + 2, vd + 128, idesc_pv, 1u);
+          if (ksteps > 2) umma_bf16_ss(tmem_O, pd + 4, vd + 256, idesc_pv, 1u);
+          if (ksteps > 3) umma_bf16_ss(tmem_O, pd + 6, vd + 384, idesc_pv, 1u);
+          umma_commit(&kv_empty[sv]);
+          umma_commit(pv_done);
+        }
+        __syncwarp();
         if (++sv == ATT_STAGES) sv = 0;
       }
     }

@@ -8,7 +8,7 @@
 // One CTA per SM, 384 threads (three warpgroups; setmaxnreg moves registers from the third to the softmax groups), ALL 512 TMEM columns, two independent "slots" that ping-pong on the tensor pipe:
 //   warps 0..3  softmax of slot A      warps 4..7  softmax of slot B      (thread = query row = TMEM lane)
 //   warp 8      TMA producer: Q tile(s) once, then K_j / V_j tiles of 128 keys through a 4-stage ring
-//   warp 9      MMA issuer (one thread): S_t = Q_t K_j^T (M=128, N<=128, K=64, SS) -> TMEM;  O_t += P_t V_j with the A
+//   warps 9,10  MMA issuers, one thread per slot: S_t = Q_t K_j^T (M=128, N<=128, K=64, SS) -> TMEM;  O_t += P_t V_j with the A
 //               operand P_t read from TENSOR MEMORY (tcgen05.mma with a TMEM A operand, 8 x K=16) and V consumed in
 //               place from its [key][64] tile as an MN-major B operand
 // TMEM per slot (256 columns): S fp32 [128 x 128] | P bf16 [128 x 128] packed two per column (64 columns) | O fp32
@@ -34,7 +34,7 @@ namespace uvlt {
 
 constexpr int AT2_BQ = 128;
 constexpr int AT2_BK = 128;
-constexpr int AT2_THREADS = 384;  // three warpgroups: softmax A, softmax B, {TMA, MMA, two idle warps}
+constexpr int AT2_THREADS = 384;  // three warpgroups: softmax A, softmax B, {TMA, MMA A, MMA B, idle}
 constexpr int AT2_STAGES = 4;  // SPLIT mode keeps four K/V tiles in flight: (step i, i+1) x (slot A, B)
 
 struct Attn2Smem {
@@ -57,6 +57,7 @@ struct Attn2Params {
   const float* bias;
   __nv_bfloat16* out;
   int split_all;  // 1: every CTA runs ONE query tile in SPLIT mode (small grids); 0: PAIR mode, odd last tile SPLIT
+  int zero;       // always 0: an opaque branch condition that separates scheduling regions (see at2_chunk_ex2)
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = lanes, K = 16 bf16 = 8 packed 32-bit columns) is read
@@ -125,64 +126,46 @@ __device__ __forceinline__ float at2_chunk_max(const uint32_t (&v)[32], float sc
   return m;
 }
 
-// Ordered variants (asm volatile keeps their relative order through ptxas) for the software-pipelined softmax below.
-__device__ __forceinline__ float ex2_ordered(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float add_ordered(float a, float b) {
-  float y;
-  asm volatile("add.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack_ordered(float lo, float hi) {
-  uint32_t y;
-  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
-  return y;
-}
-
-// probabilities of one 32-column chunk -> 16 packed bf16 pairs; returns the fp32 row-sum contribution.
+// The softmax of a 32-column chunk in two separately scheduled halves.  Written as "p = ex2(x); sum += p; pack(p)" ptxas
+// places every consumer two instructions behind its MUFU whatever the source order (it also reorders volatile asm), and
+// the in-order warp then stalls for the MUFU latency on every column: 16.5 cycles per column measured with the warp alone
+// on its scheduler (in-kernel timeline, profiles/r02_attention.md) against the 8 the MUFU pipe needs.  So the
+// exponentials are written back IN PLACE by at2_chunk_ex2 and consumed by at2_chunk_sum_pack one basic block later (the
+// caller separates them with a branch ptxas cannot see through): MUFUs issue back to back, and a chunk's sums / packs
+// fill the issue slots under the next chunk's MUFUs.
+// MODE 0: full unbiased block.  MODE 2: partial and / or biased block (sb = shared address of this chunk's bias * log2e;
+// scale and reference in ONE fma exactly as in mode 0 and the bias added afterwards, so a key whose bias is 0 gets
+// bit-identical probabilities whichever mode its block runs in -- engine option skip_text).
 // POLY: every fourth column takes the FMA-pipe exponential.
-// Software pipelined with a distance of eight columns: the exponential of column i is issued, THEN the sum / pack of
-// column i-8.  Left to itself ptxas puts each FADD right behind its MUFU (whatever the source order) and the warp stalls
-// for the full MUFU latency on every column: ~17 cycles per column instead of the 8 the MUFU pipe needs (this is what
-// bounded the first-generation kernel's softmax as well, profiles/r01_attention_experiments.md); the volatile asm
-// statements keep their order.
 template <int MODE, bool POLY>
-__device__ __forceinline__ float at2_chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], float scale, float neg_ref,
-                                               uint32_t sb, int lim) {
-  constexpr int DIST = 8;
-  float e[2 * DIST];
-  float s0 = 0.f, s1 = 0.f;
+__device__ __forceinline__ void at2_chunk_ex2(uint32_t (&v)[32], float scale, float neg_ref, uint32_t sb, int lim) {
 #pragma unroll
-  for (int i = 0; i < 32 + DIST; ++i) {
-    if (i < 32) {
-      float x = fmaf(__uint_as_float(v[i]), scale, neg_ref);
-      // MODE 2: scale and reference in ONE fma exactly as in the unbiased mode, the bias added afterwards: a key whose
-      // bias is 0 gets bit-identical probabilities whichever mode its block runs in (engine option skip_text)
-      if (MODE == 2) x += lds_f32(sb + i * 4);
-      float y = (POLY && (i & 3) == 3) ? ex2_poly3(x) : ex2_ordered(x);
-      if (MODE != 0) y = i < lim ? y : 0.0f;  // stale TMEM columns past the last real key must not reach P
-      e[i % (2 * DIST)] = y;
-    }
-    const int c = i - DIST;
-    if (c >= 0) {
-      if (c & 1) {
-        const float p0 = e[(c - 1) % (2 * DIST)], p1 = e[c % (2 * DIST)];
-        s1 = add_ordered(s1, p1);
-        pk[c >> 1] = pack_ordered(p0, p1);
-      } else {
-        s0 = add_ordered(s0, e[c % (2 * DIST)]);
-      }
-    }
+  for (int i = 0; i < 32; ++i) {
+    float x = fmaf(__uint_as_float(v[i]), scale, neg_ref);
+    if (MODE == 2) x += lds_f32(sb + i * 4);
+    float y = (POLY && (i & 3) == 3) ? ex2_poly3(x) : ex2_approx(x);
+    if (MODE != 0) y = i < lim ? y : 0.0f;  // stale TMEM columns past the last real key must not reach P
+    v[i] = __float_as_uint(y);
   }
-  return s0 + s1;
+}
+__device__ __forceinline__ float at2_chunk_sum_pack(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    s0 += __uint_as_float(v[i]);
+    s1 += __uint_as_float(v[i + 1]);
+    s2 += __uint_as_float(v[i + 2]);
+    s3 += __uint_as_float(v[i + 3]);
+    pk[i >> 1] = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    pk[(i >> 1) + 1] = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+  }
+  return (s0 + s1) + (s2 + s3);
 }
 
 template <bool POLY>
 static __global__ void __launch_bounds__(AT2_THREADS, 1)
-attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params p) {
+attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out,
+                  const Attn2Params p) {
   extern __shared__ __align__(1024) uint8_t att2_smem[];
   uint8_t* const smem = att2_smem;
   uint8_t* const sQ = smem + Attn2Smem::OFF_Q;
@@ -195,14 +178,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
   uint64_t* const s_free = s_full + 2;                // [2] the slot's 4 softmax warps hold S_t in registers
   uint64_t* const p_full = s_free + 2;                // [2] P_t stored (and O_t rescaled)
   uint64_t* const pv_done = p_full + 2;               // [2] PV_t drained: P_t reusable, O_t includes the block
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* const stagger = pv_done + 2;              // slot A is half way through its first block (4 warp arrivals)
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int D = p.H * ATT_D;
   const int nblk = (p.n + AT2_BK - 1) / AT2_BK;
+  TRACE_DECL;
+  if (lane == 0) TRACE_PT(0x200 + warp);
   const int ntiles = (p.n + AT2_BQ - 1) / AT2_BQ;
   // ---- slot configuration (uniform over the CTA) ----
   const int tile0 = p.split_all ? blockIdx.x : 2 * blockIdx.x;
@@ -220,6 +206,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
   if (warp == 8 && lane == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_out);
     mbar_init(&q_full[0], 1);
     mbar_init(&q_full[1], 1);
     for (int s = 0; s < AT2_STAGES; ++s) {
@@ -232,6 +219,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
       mbar_init(&p_full[t], 4);
       mbar_init(&pv_done[t], 1);
     }
+    mbar_init(stagger, 4);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -250,14 +238,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_expect_tx(&q_full[0], Attn2Smem::Q_BYTES);
-      tma_load_3d(sQ, &tma_qkv, &q_full[0], h * ATT_D, q0A, b);
-      if (!lone) {
-        mbar_expect_tx(&q_full[1], Attn2Smem::Q_BYTES);
-        tma_load_3d(sQ + Attn2Smem::Q_BYTES, &tma_qkv, &q_full[1], h * ATT_D, q0B, b);
+    {
+      // ---------------- TMA producer (converged warp, one elected lane issues) ----------------
+      if (elect_one_sync()) {
+        mbar_expect_tx(&q_full[0], Attn2Smem::Q_BYTES);
+        tma_load_3d(sQ, &tma_qkv, &q_full[0], h * ATT_D, q0A, b);
+        if (!lone) {
+          mbar_expect_tx(&q_full[1], Attn2Smem::Q_BYTES);
+          tma_load_3d(sQ + Attn2Smem::Q_BYTES, &tma_qkv, &q_full[1], h * ATT_D, q0B, b);
+        }
       }
+      __syncwarp();
       int c = 0;
 #pragma unroll 1
       for (int i = 0; i < steps; ++i) {
@@ -268,68 +259,86 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
           const int s = c % AT2_STAGES;
           const uint32_t ph = (c / AT2_STAGES) & 1;
           mbar_wait_trap(&kv_empty[s], ph ^ 1);
-          uint8_t* const dst = sKV + s * Attn2Smem::STAGE_BYTES;
-          mbar_expect_tx(&kv_full[s], Attn2Smem::STAGE_BYTES);
-          tma_load_3d(dst, &tma_qkv, &kv_full[s], D + h * ATT_D, j * AT2_BK, b);
-          tma_load_3d(dst + Attn2Smem::KV_BYTES, &tma_qkv, &kv_full[s], 2 * D + h * ATT_D, j * AT2_BK, b);
+          if (elect_one_sync()) {
+            uint8_t* const dst = sKV + s * Attn2Smem::STAGE_BYTES;
+            mbar_expect_tx(&kv_full[s], Attn2Smem::STAGE_BYTES);
+            tma_load_3d(dst, &tma_qkv, &kv_full[s], D + h * ATT_D, j * AT2_BK, b);
+            tma_load_3d(dst + Attn2Smem::KV_BYTES, &tma_qkv, &kv_full[s], 2 * D + h * ATT_D, j * AT2_BK, b);
+          }
+          __syncwarp();
           ++c;
         }
       }
     }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+  } else if (warp == 9 || warp == 10) {
+    {
+      // ---------------- MMA issuer of slot t (one converged warp per slot, one elected lane issues) ----------------
+      // One issuer per slot: with a single thread walking [QK_A, QK_B, PV_A, PV_B] in a fixed order, each slot's PV waits
+      // for the OTHER slot's softmax and the two slots fall into lock step -- both in their exponentials (tensor pipe
+      // idle), then both waiting for their PV (MUFU idle): 36 % of the softmax warps' samples sat in s_full / pv_done
+      // waits (ncu source view, profiles/r02_attention.md).  The tensor pipe interleaves the two threads' instructions.
+      const int t = warp - 9;
+      const int ns = ns_of(t), jb = jb_of(t);
       const int last_valid = p.n - (nblk - 1) * AT2_BK;  // keys in the sequence's last block
       const uint32_t idesc_full = umma_idesc_bf16(AT2_BQ, AT2_BK, 0);
       const uint32_t idesc_last = umma_idesc_bf16(AT2_BQ, (last_valid + 15) & ~15, 0);  // UMMA N granularity 16
       constexpr uint32_t idesc_pv = umma_idesc_bf16(AT2_BQ, ATT_D, 1);
-      const uint64_t qd0 = umma_smem_desc_sw128(smem_u32(sQ), 1024, 0);
-      const uint64_t qd1 = umma_smem_desc_sw128(smem_u32(sQ + (lone ? 0 : Attn2Smem::Q_BYTES)), 1024, 0);
+      const uint64_t qd = umma_smem_desc_sw128(smem_u32(sQ + ((lone || t == 0) ? 0 : Attn2Smem::Q_BYTES)), 1024, 0);
       const uint64_t kd_base = umma_smem_desc_sw128(smem_u32(sKV), 1024, 0);
       // V: [key][64] rows of 128 B = MN-major B operand; 16 keys = 16 rows = 2048 B (+128 in the 16-byte address field)
       const uint64_t vd_base = umma_smem_desc_sw128(smem_u32(sKV + Attn2Smem::KV_BYTES), 1024, 1024);
       constexpr uint64_t STAGE_STEP = Attn2Smem::STAGE_BYTES >> 4;
-      auto issue_qk = [&](int i, int t) {
+      const uint32_t tS = tmem_base + t * 256;
+      const uint32_t tP = tS + 128;
+      const uint32_t tO = tS + 192;
+      auto issue_qk = [&](int i) {
         const int c = ring_pos(i, t);
         mbar_wait_trap(&kv_full[c % AT2_STAGES], (c / AT2_STAGES) & 1);
         if (i > 0) mbar_wait_trap(&s_free[t], (i - 1) & 1);  // the softmax warps hold S_t(i-1) in registers
         tc_fence_after();
         const uint64_t kd = kd_base + STAGE_STEP * (c % AT2_STAGES);
-        const uint32_t idesc = (jb_of(t) + i == nblk - 1) ? idesc_last : idesc_full;
-        const uint32_t tS = tmem_base + t * 256;
-        const uint64_t qd = t ? qd1 : qd0;
-        umma_bf16_ss(tS, qd, kd, idesc, 0u);
-        umma_bf16_ss(tS, qd + 2, kd + 2, idesc, 1u);
-        umma_bf16_ss(tS, qd + 4, kd + 4, idesc, 1u);
-        umma_bf16_ss(tS, qd + 6, kd + 6, idesc, 1u);
-        umma_commit(&s_full[t]);
+        const uint32_t idesc = (jb + i == nblk - 1) ? idesc_last : idesc_full;
+        if (elect_one_sync()) {
+          umma_bf16_ss(tS, qd, kd, idesc, 0u);
+          umma_bf16_ss(tS, qd + 2, kd + 2, idesc, 1u);
+          umma_bf16_ss(tS, qd + 4, kd + 4, idesc, 1u);
+          umma_bf16_ss(tS, qd + 6, kd + 6, idesc, 1u);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+        if (lane == 0) TRACE_PT(0x300 + t * 0x100 + 0x10 + i);  // QK(i) issued
       };
-      mbar_wait_trap(&q_full[0], 0);
-      if (!lone) mbar_wait_trap(&q_full[1], 0);
+      if (ns > 0) {
+        mbar_wait_trap(&q_full[(lone || t == 0) ? 0 : 1], 0);
+        // PAIR mode: start slot B half a block behind slot A, so that one slot's exponentials (MUFU) run under the other
+        // slot's TMEM loads, maximum, barrier round trips and MMAs instead of both doing the same thing at the same time
+        if (!lone && t == 1) mbar_wait_trap(stagger, 0);
+        issue_qk(0);
+      }
 #pragma unroll 1
-      for (int t = 0; t < 2; ++t)
-        if (ns_of(t) > 0) issue_qk(0, t);
+      for (int i = 0; i < ns; ++i) {
+        if (i + 1 < ns) issue_qk(i + 1);
+        mbar_wait_trap(&p_full[t], i & 1);
+        tc_fence_after();
+        if (lane == 0) TRACE_PT(0x300 + t * 0x100 + 0x20 + i);  // p_full(i) seen
+        const int c = ring_pos(i, t);
+        const uint64_t vd = vd_base + STAGE_STEP * (c % AT2_STAGES);
+        const int ksteps = (jb + i == nblk - 1) ? ((last_valid + 15) >> 4) : (AT2_BK / 16);
+        if (elect_one_sync()) {
+          if (ksteps == AT2_BK / 16) {
+#pragma unroll
+            for (int k = 0; k < AT2_BK / 16; ++k) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
+          } else {
 #pragma unroll 1
-      for (int i = 0; i < steps; ++i) {
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t)
-          if (i + 1 < ns_of(t)) issue_qk(i + 1, t);
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          if (i >= ns_of(t)) continue;
-          mbar_wait_trap(&p_full[t], i & 1);
-          tc_fence_after();
-          const int c = ring_pos(i, t);
-          const int ksteps = (jb_of(t) + i == nblk - 1) ? ((last_valid + 15) >> 4) : (AT2_BK / 16);
-          const uint64_t vd = vd_base + STAGE_STEP * (c % AT2_STAGES);
-          const uint32_t tP = tmem_base + t * 256 + 128;
-          const uint32_t tO = tmem_base + t * 256 + 192;
-#pragma unroll 1
-          for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&kv_empty[c % AT2_STAGES]);
           umma_commit(&pv_done[t]);
         }
+        __syncwarp();
+        if (lane == 0) TRACE_PT(0x300 + t * 0x100 + 0x30 + i);  // PV(i) issued
       }
+      if (lane == 0) TRACE_FLUSH();
     }
   }
   } else {
@@ -374,6 +383,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
       uint32_t v[4][32], pk[16];
       mbar_wait_trap(&s_full[t], i & 1);
       tc_fence_after();
+      if (lane == 0 && quad == 0) TRACE_PT(0x500 + t * 0x100 + 0x10 + i);  // s_full(i) seen
       tmem_ld64(tS, v[0], v[1]);
       tmem_ld64(tS + 64, v[2], v[3]);
       tmem_wait_ld_dep2(v[0], v[1]);
@@ -381,6 +391,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);  // QK of the slot's next block may overwrite S
+      if (lane == 0 && quad == 0) TRACE_PT(0x500 + t * 0x100 + 0x20 + i);  // S in registers
 
       // ---- block maximum and the exp reference ----
       float m_blk;
@@ -399,37 +410,57 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
       const float ref = (m_blk > m_run + 8.0f) ? m_blk : m_run;  // m_run = -inf on the first block -> m_blk
       const float alpha = (ref == m_run) ? 1.0f : ex2_approx(m_run - ref);  // 0 on the first block
       const float neg_ref = -ref;
+      // ---- exponentials (in place) one chunk ahead of the sums / packs / P stores; `p.zero` (always 0) gives ptxas a
+      //      branch between the stages, i.e. separate scheduling regions (see at2_chunk_ex2) ----
       float l_blk = 0.0f;
+      auto ex2_chunk = [&](int c) {
+        if (c >= nchunk) return;
+        if (mode == 0) at2_chunk_ex2<0, POLY>(v[c], scale, neg_ref, 0, 32);
+        else at2_chunk_ex2<2, false>(v[c], scale, neg_ref, sbj + c * 128, kv_valid - c * 32);
+      };
+      auto store_chunk = [&](int c) {
+        if (c >= nchunk) return;
+        l_blk += at2_chunk_sum_pack(v[c], pk);
+        tmem_st16(tP + c * 16, pk);
+      };
+      ex2_chunk(0);
+      if (p.zero) break;
+      ex2_chunk(1);
+      if (i == 0 && t == 0 && lane == 0) mbar_arrive(stagger);  // PAIR mode: slot B starts half a block behind slot A
+      if (i > 0) {
+        // P_t and O_t are free once PV_t(i-1) has drained (two chunks of exponentials were computed meanwhile)
+        if (lane == 0 && quad == 0) TRACE_PT(0x500 + t * 0x100 + 0x30 + i);  // max + two chunks done
+        mbar_wait_trap(&pv_done[t], (i - 1) & 1);
+        tc_fence_after();
+        if (lane == 0 && quad == 0) TRACE_PT(0x500 + t * 0x100 + 0x40 + i);  // pv_done(i-1) seen
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // bring the running output to the new reference (rare)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nchunk) {
-          if (mode == 0) l_blk += at2_chunk_exp<0, POLY>(v[c], pk, scale, neg_ref, 0, 32);
-          else l_blk += at2_chunk_exp<2, false>(v[c], pk, scale, neg_ref, sbj + c * 128, kv_valid - c * 32);
-        }
-        if (c == 0 && i > 0) {
-          // P_t and O_t are free once PV_t(i-1) has drained (the first chunk's exponentials were computed meanwhile)
-          mbar_wait_trap(&pv_done[t], (i - 1) & 1);
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // bring the running output to the new reference (rare)
+          for (int cc = 0; cc < ATT_D; cc += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc, o);
+            tmem_wait_ld();
 #pragma unroll
-            for (int cc = 0; cc < ATT_D; cc += 32) {
-              uint32_t o[32];
-              tmem_ld32(tO + cc, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
-              tmem_st32(tO + cc, o);
-            }
+            for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+            tmem_st32(tO + cc, o);
           }
         }
-        if (c < nchunk) tmem_st16(tP + c * 16, pk);
       }
+      store_chunk(0);
+      if (p.zero) break;
+      ex2_chunk(2);
+      store_chunk(1);
+      if (p.zero) break;
+      ex2_chunk(3);
+      store_chunk(2);
+      if (p.zero) break;
+      store_chunk(3);
       l_run = l_run * alpha + l_blk;
       m_run = ref;
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0 && quad == 0) TRACE_PT(0x500 + t * 0x100 + 0x50 + i);  // P stored
     }
     // ---------------- epilogue: O / l -> bf16 ----------------
     if (ns > 0) {
@@ -465,7 +496,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
       }
     }
     if (!lone || t == 0) {
-      const int q = q0_of(t) + row;
+      uint8_t* const stage = sQ + ((lone || t == 0) ? 0 : Attn2Smem::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < ATT_D; c += 32) {
         uint32_t o[32];
@@ -481,21 +512,34 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const Attn2Params
             o[i + 3] = __float_as_uint(__uint_as_float(o[i + 3]) * a_own + x.w * a_peer);
           }
         }
-        if (q < p.n) {
-          __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.n + q) * D + h * ATT_D + c;
+        // bf16 row -> staging tile in the slot's (no longer needed) Q buffer, 16-byte chunks XOR-swizzled with row % 8:
+        // that IS the 128B-swizzle TMA layout, and the writes are bank-conflict free
+        uint8_t* const st_row = stage + row * 128;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + i) = u;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(st_row + ((((c + i) >> 3) ^ (row & 7)) << 4)) = u;
         }
+      }
+      // one TMA bulk store per tile (rows >= n are clipped by the tensor map): the row-per-thread global stores of the
+      // first version cost ~4k cycles per CTA (32 L1 wavefronts per instruction)
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + t) : "memory");
+      if (quad == 0 && lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tma_out)),
+                     "r"(smem_u32(stage)), "r"(h * ATT_D), "r"(q0_of(t)), "r"(b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes are complete before the CTA exits
       }
     }
     tc_fence_before();
+    if (lane == 0 && quad == 0) { TRACE_PT(0x500 + t * 0x100 + 0x60); TRACE_FLUSH(); }
   }
 
   __syncthreads();

@@ -30,6 +30,26 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The tcgen05 / TMA instructions take their operands from uniform registers:
+// issued under `if (lane == 0)` the warp is divergent as far as ptxas knows, every operand lives in a per-thread register
+// and each instruction is wrapped in an ELECT + R2UR.BROADCAST waterfall loop (150-300 cycles per tcgen05.mma measured in
+// the attention timeline, profiles/r02_attention.md).  Keeping the issuing warp converged -- uniform loop counters and
+// barrier waits on all 32 lanes, only the asynchronous instruction itself under elect_one_sync() -- lets ptxas keep the
+// descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value ptxas knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

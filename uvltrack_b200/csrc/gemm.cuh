@@ -257,7 +257,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + ring_bytes + S::BAR_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * GEMM_BM;
@@ -272,22 +272,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (threadIdx.x == 0) TRACE_PT(0x100);
 
   // ---- prologue: touches only weights (W tiles, bias), so under PDL it overlaps the predecessor kernel ----
-  if (warp == 0 && lane == 0) {
-    if (smem_u32(smem) & 1023u) __trap();  // dynamic shared memory must be 1024-byte aligned
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_w);
+  if (warp == 0) {
+    if (lane == 0) {
+      if (smem_u32(smem) & 1023u) __trap();  // dynamic shared memory must be 1024-byte aligned
+      tma_prefetch_desc(&tma_a);
+      tma_prefetch_desc(&tma_w);
 #pragma unroll 1
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MC ? 2 : 1);
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], MC ? 2 : 1);
+      }
+      mbar_init(acc_bar, 1);
+      fence_mbar_init();
     }
-    mbar_init(acc_bar, 1);
-    fence_mbar_init();
+    __syncwarp();
+    if (elect_one_sync()) {
 #pragma unroll 1
-    for (int kb = 0; kb < pre; ++kb) {
-      mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);  // A + W bytes; the A half is issued after pdl_wait
-      tma_load_3d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tma_w, &full_bar[kb], (kb0 + kb) * GEMM_BK, n0, g);
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);  // A + W bytes; the A half is issued after pdl_wait
+        tma_load_3d(smem + kb * S::STAGE_BYTES + S::A_BYTES, &tma_w, &full_bar[kb], (kb0 + kb) * GEMM_BK, n0, g);
+      }
     }
+    __syncwarp();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -307,35 +313,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   pdl_trigger();
   if (threadIdx.x == 0) TRACE_PT(0x102);
 
+  // The producer and MMA warps stay CONVERGED (uniform loop counters, all lanes wait on the barriers) and only the
+  // asynchronous instruction is issued by one elected lane: under `if (lane == 0)` ptxas wraps every tcgen05.mma / TMA
+  // instruction in an ELECT + R2UR.BROADCAST waterfall loop (see elect_one_sync in common.cuh).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------- TMA producer ----------------
+      if (elect_one_sync()) {
 #pragma unroll 1
-      for (int kb = 0; kb < pre; ++kb) {
-        if (MC)
-          tma_load_3d_mc(smem + kb * S::STAGE_BYTES + crank * A_HALF, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK,
-                         m0 + crank * (GEMM_BM / 2), g, 0x3);
-        else
-          tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
+        for (int kb = 0; kb < pre; ++kb) {
+          if (MC)
+            tma_load_3d_mc(smem + kb * S::STAGE_BYTES + crank * A_HALF, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK,
+                           m0 + crank * (GEMM_BM / 2), g, 0x3);
+          else
+            tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
+        }
       }
+      __syncwarp();
       int s = 0;              // pre == STAGES whenever the loop below runs
       uint32_t ph = 0;
 #pragma unroll 1
       for (int kb = pre; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph);
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        if (MC)
-          tma_load_3d_mc(a_dst + crank * A_HALF, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0 + crank * (GEMM_BM / 2), g,
-                         0x3);
-        else
-          tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
-        tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, g);
+        if (elect_one_sync()) {
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+          if (MC)
+            tma_load_3d_mc(a_dst + crank * A_HALF, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0 + crank * (GEMM_BM / 2), g,
+                           0x3);
+          else
+            tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
+          tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, g);
+        }
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0);
       int s = 0;
@@ -344,23 +359,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (kb == 0) TRACE_PT(0x103);
+        if (kb == 0 && lane == 0) TRACE_PT(0x103);
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b_addr = a_addr + S::A_BYTES;
         const uint64_t adesc = umma_smem_desc_sw128(a_addr, 1024, 0);
         const uint64_t bdesc = umma_smem_desc_sw128(b_addr, 1024, 0);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16_ss(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16_ss(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          // frees the smem slot (in both CTAs of the cluster) when these MMAs have drained
+          if (MC) umma_commit_mc(&empty_bar[s], 0x3);
+          else umma_commit(&empty_bar[s]);
+          if (kb == num_kb - 1) umma_commit(acc_bar);  // accumulator complete
         }
-        // frees the smem slot (in both CTAs of the cluster) when these MMAs have drained
-        if (MC) umma_commit_mc(&empty_bar[s], 0x3);
-        else umma_commit(&empty_bar[s]);
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(acc_bar);  // accumulator complete
-      TRACE_PT(0x104);
+      if (lane == 0) TRACE_PT(0x104);
     }
   } else {
     // ---------------- epilogue warps ----------------
@@ -424,7 +442,7 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_zero = reinterpret_cast<float*>(stage_base + GEMM2_EPI_BYTES + 256);  // bias of a bias-less GEMM
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs)
   const int num_kb = shape.K / GEMM_BK;
@@ -476,8 +494,8 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer (both CTAs) ----------------
+    {
+      // ---------------- TMA producer (both CTAs; converged warp, one elected lane issues) ----------------
       int s = 0;
       uint32_t ph = 1;  // fresh barriers: the first pass over the ring does not wait
 #pragma unroll 1
@@ -487,17 +505,20 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph);  // the leader's MMAs have drained this slot in BOTH CTAs
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
-          if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-          tma_load_3d_2sm(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
-          tma_load_3d_2sm(a_dst + A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0 + static_cast<int>(crank) * (BN / 2), g);
+          if (elect_one_sync()) {
+            uint8_t* a_dst = smem + s * STAGE_BYTES;
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            tma_load_3d_2sm(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
+            tma_load_3d_2sm(a_dst + A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0 + static_cast<int>(crank) * (BN / 2), g);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
-      // ---------------- MMA issuer (leader only) ----------------
+    if (crank == 0) {
+      // ---------------- MMA issuer (leader only; converged warp, one elected lane issues) ----------------
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, 0);
       int s = 0;
       uint32_t ph = 0;
@@ -512,18 +533,21 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (it == 0 && kb < 2) TRACE_PT(0x103);
+          if (it == 0 && kb < 2 && lane == 0) TRACE_PT(0x103);
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc_sw128(a_addr, 1024, 0);
           const uint64_t bdesc = umma_smem_desc_sw128(a_addr + A_BYTES, 1024, 0);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16_ss_2sm(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[s], 0x3);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              umma_bf16_ss_2sm(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[s], 0x3);
+            if (kb == num_kb - 1) umma_commit_2sm(&acc_full[buf], 0x3);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(&acc_full[buf], 0x3);
-        if (it < 4) TRACE_PT(0x104);
+        if (it < 4 && lane == 0) TRACE_PT(0x104);
       }
     }
   } else {

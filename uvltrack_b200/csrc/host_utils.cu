@@ -60,15 +60,20 @@ static int g_attn_split = [] {
   return (e && e[0] == '0') ? 0 : 1;
 }();
 
-// UVLT_ATTN_V=1 selects the first-generation attention kernel (attention.cuh) for A/B timing; default: attention2.cuh.
-// UVLT_ATTN_POLY=0 keeps every exponential on the MUFU.
+// UVLT_ATTN_V=2 selects the second-generation attention kernel (attention2.cuh: P in tensor memory, two slots per CTA).
+// Measured on B200 (tools/kernel_sweep.py attn, profiles/r02_attention.md), us per launch, v1 / v2:
+//   B=32: n=553 77.1 / 92.4, n=513 73.2 / 88.4, n=361 35.5 / 50.9      B=8: n=553 26.8 / 24.5, n=361 13.8 / 17.2
+//   B=1:  n=553 8.4 / 8.2, n=513 7.7 / 8.2, n=361 7.4 / 6.6
+// v1 (three CTAs per SM, 64-key blocks) hides its per-block latency chain across CTAs and stays the default; v2 is one
+// CTA per SM and pays ~8k cycles of set-up / drain per CTA that a persistent work loop would hide (next step).
+// UVLT_ATTN_POLY=1: a quarter of v2's exponentials on the FMA pipe (no gain while the kernel is not MUFU bound).
 static int g_attn_v = [] {
   const char* e = getenv("UVLT_ATTN_V");
-  return (e && e[0] == '1') ? 1 : 2;
+  return (e && e[0] == '2') ? 2 : 1;
 }();
 static int g_attn_poly = [] {
   const char* e = getenv("UVLT_ATTN_POLY");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] == '1') ? 1 : 0;
 }();
 
 int init_kernel_attributes() {
@@ -354,6 +359,10 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   a->p2.scale_log2 = a->p.scale_log2;
   a->p2.bias = bias;
   a->p2.out = a->p.out;
+  a->p2.zero = 0;
+  if (make_tma_bf16_3d(&a->tma_o, out, static_cast<uint64_t>(H) * ATT_D, n, B, static_cast<uint64_t>(H) * ATT_D * 2,
+                       static_cast<uint64_t>(n) * H * ATT_D * 2, AT2_BQ))
+    return 1;
   // small grids (decided from the engine's capacity, so that a sequence's result does not depend on the batch it shares
   // a call with): one query tile per CTA, the two slots split its key blocks
   a->p2.split_all = (g_attn_split && cb * H * ((n + AT2_BQ - 1) / AT2_BQ) <= g_num_sms) ? 1 : 0;
@@ -364,8 +373,8 @@ int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   if (a.v2) {
     const int ntiles = (a.p2.n + AT2_BQ - 1) / AT2_BQ;
     dim3 grid2(a.p2.split_all ? ntiles : (ntiles + 1) / 2, a.p2.H, a.B);
-    if (a.poly) UVLT_LAUNCH(attention2_kernel<true>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.p2);
-    else UVLT_LAUNCH(attention2_kernel<false>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.p2);
+    if (a.poly) UVLT_LAUNCH(attention2_kernel<true>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p2);
+    else UVLT_LAUNCH(attention2_kernel<false>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p2);
     UVLT_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -68,6 +68,7 @@ struct AttnLaunch {
   bool v2;
   bool poly;   // a quarter of the exponentials on the FMA pipe
   Attn2Params p2;
+  CUtensorMap tma_o;  // output [B, n, H*64] bf16, 128-row boxes (TMA bulk store of a query tile)
 };
 // capacity_batch: the batch size the split decision is made for (the engine passes its max_batch, so that a sequence's
 // result does not depend on how many sequences share the call; 0 = use B)
