@@ -139,6 +139,14 @@ UVLT_API int uvlt_forward_prompt(uvlt_handle h, const float* tokens, const int64
                                  const uint8_t* template_mask, const uint8_t* context_mask, int32_t batch,
                                  float* prompt_out, void* stream);
 
+/* ModalityAdaptiveBoxHead.forward (lib/models/heads/modality_adaptive_box_head.py:62-94), test branch (the prompt is given,
+ * :140-148): conv towers, contrastive score against the prompt, convert2bbox.
+ *   search_tokens fp32 [B, Nx, D] = backbone_info['search'] (NULL: the search rows of the token stream the last
+ *   uvlt_backbone / forward on this handle left in the engine), prompt fp32 [B,3,D], flag int64 [B]: device pointers.
+ * Fills out->cls_score / bbox_map / pred_boxes / cont_score / cont_prob / prompts. */
+UVLT_API int uvlt_head(uvlt_handle h, const float* search_tokens, const float* prompt, const int64_t* flag, int32_t batch,
+                       uvlt_outputs* out, void* stream);
+
 /* Post-processing of Tracker.track (lib/test/tracker/uvltrack.py:116-121,127-130) on the maps of the last forward:
  * merge = cls * window * softmax(cont)[...,0] in float64, argmax, gather.
  *   window: device float64 [S*S] (np.outer(np.hanning(S), np.hanning(S)), tracker :64-68)

@@ -34,8 +34,24 @@ WORKER = textwrap.dedent("""
     n_seq, T = 5, 7                                   # ragged: rank 0 owns 3 sequences, rank 1 owns 2
     lo, hi = dp.shard_range(n_seq, rank, world)
     full = torch.arange(n_seq * T * 4, dtype=torch.float32).reshape(n_seq, T, 4)
+    calls = []
+    for name in ("all_gather", "all_gather_into_tensor", "all_reduce", "broadcast", "all_to_all"):
+        orig = getattr(dist, name)
+        setattr(dist, name, (lambda o, n: (lambda *a, **k: (calls.append(n), o(*a, **k))[1]))(orig, name))
     got = dp.gather_trajectories(full[lo:hi].clone(), n_sequences=n_seq)
     assert torch.equal(got, full), (rank, got.shape)
+    assert calls == ["all_gather"], calls            # ONE collective: shard sizes come from shard_range, not a reduce
+    # equal shards (the benchmark's layout) and the warm-up gather before a timed region
+    del calls[:]
+    eq = torch.arange(2 * 3 * T * 4, dtype=torch.float32).reshape(6, T, 4)
+    dp.warmup_gather(eq[:3])
+    got = dp.gather_trajectories(eq[3 * rank: 3 * rank + 3].clone(), n_sequences=6)
+    assert torch.equal(got, eq) and calls == ["all_gather", "all_gather"], calls
+    try:
+        dp.gather_trajectories(eq[:2].clone(), n_sequences=6)   # a shard that disagrees with shard_range is an error
+        raise SystemExit("expected RuntimeError")
+    except RuntimeError:
+        pass
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")

@@ -70,6 +70,54 @@ def test_sequence_failures_are_swallowed_unless_debugging(tmp_path):
     ev.run_dataset([_seq("s1", 3), _seq("s2", 2)], [tr])                   # both fail at frame 2 / none -> no crash
 
 
+class _FakeBatchTracker:
+    """BatchTracker stand-in (CPU): sequence 'tiny' fails with the reference's 'Too small bounding box.' at frame 3."""
+
+    def __init__(self, params, batch=1):
+        self.B, self.state, self.failed, self.n, self.names = batch, None, None, 0, None
+
+    def initialize(self, images, infos):
+        self.state = [list(i["init_bbox"]) for i in infos]
+        self.names = [i["seq_name"] for i in infos]
+        self.failed = [None] * self.B
+        self.n = 0
+
+    def track(self, images, raise_on_failure=True):
+        self.n += 1
+        out = []
+        for b in range(self.B):
+            if self.names[b] == "tiny" and self.n >= 3:
+                self.failed[b] = "Too small bounding box."
+            if self.failed[b]:
+                assert not raise_on_failure
+                out.append({"target_bbox": self.state[b], "failed": True, "error": self.failed[b]})
+                continue
+            self.state[b] = [self.state[b][0] + 1.0] + self.state[b][1:]
+            out.append({"target_bbox": list(self.state[b])})
+        return out
+
+
+def test_batched_scheduler_isolates_failures(tmp_path, monkeypatch):
+    """a failing sequence (tiny box, unreadable frame) must cost that sequence only -- the reference's
+    run_sequence swallows the exception per sequence (running.py:124-128); healthy co-batched sequences are saved and the
+    rest of the shard goes on."""
+    import uvltrack_b200.tracker as trk
+
+    monkeypatch.setattr(trk, "BatchTracker", _FakeBatchTracker)
+    params = _params()
+    bad_frames = _seq("unreadable", 5)
+    bad_frames.frames[2] = str(tmp_path / "does_not_exist.jpg")
+    first_bad = _seq("nofirst", 4)
+    first_bad.frames[0] = str(tmp_path / "missing0.jpg")
+    seqs = [_seq("ok_a", 6), _seq("tiny", 6), bad_frames, _seq("ok_b", 5), first_bad, _seq("ok_c", 3)]
+    tr = ev.Tracker("uvltrack", "baseline_base", "synth", params, str(tmp_path))
+    done = ev.run_dataset_batched(seqs, tr, batch=2)
+    assert sorted(done) == ["ok_a", "ok_b", "ok_c"]
+    assert [len(done[k]) for k in ("ok_a", "ok_b", "ok_c")] == [6, 5, 3]
+    sub = tmp_path / f"synth_BBOX_{int(params.cfg.TEST.EPOCH):03d}"
+    assert sorted(f.name for f in sub.iterdir() if not f.name.endswith("_time.txt")) == ["ok_a.txt", "ok_b.txt", "ok_c.txt"]
+
+
 @pytest.mark.gpu
 def test_batched_scheduler_matches_sequential(tmp_path, monkeypatch):
     # the batched run uses an engine of capacity 2, the sequential one capacity 1: their split-K factors differ, and with

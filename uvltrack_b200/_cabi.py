@@ -59,6 +59,7 @@ SIGNATURES = {
     "uvlt_forward_train": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, C.POINTER(UvltOutputs), _P]),
     "uvlt_backbone": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, C.POINTER(UvltOutputs), _P]),
     "uvlt_forward_prompt": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, _P, _P]),
+    "uvlt_head": (c_int, [_P, _P, _P, _P, c_int32, C.POINTER(UvltOutputs), _P]),
     "uvlt_track_decode": (c_int, [_P, _P, c_int32, _P, _P, _P, _P]),
     "uvlt_track_frame_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "uvlt_track_frame_image_host": (c_int, [_P, _P, c_int32, c_int32, _P, C.c_double, _P, _P, _P, _P, _P, _P, c_int32,

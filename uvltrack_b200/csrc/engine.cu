@@ -901,6 +901,13 @@ int uvlt_create(const uvlt_config* cfg, uvlt_handle* out) {
   e->S = e->Hx / 16; e->SS = e->S * e->S; e->F0 = cfg->fusion_start; e->C = cfg->head_channels; e->Bm = cfg->max_batch;
   if (e->N > ATT_MAX_KV) { set_error("sequence too long for the attention kernel"); delete e; return 1; }
   cudaGetDevice(&e->device);
+  // dynamic shared memory above 48 KB needs an opt-in per kernel AND per device (D = 1024 with Nz + Nx >= ~1800 rows)
+  if (cudaFuncSetAttribute(prompter_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(prompter_smem_bytes(1024, PROMPTER_MAX_N))) != cudaSuccess) {
+    set_error("uvlt_create: cudaFuncSetAttribute(prompter_pool_kernel) failed");
+    delete e;
+    return 1;
+  }
   if (init_kernel_attributes() || alloc_activations(e) ||
       cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1067,6 +1074,29 @@ int uvlt_forward_prompt(uvlt_handle e, const float* tokens, const int64_t* flag,
   e->launch_count = 0;
   return run_prompter(e, p, static_cast<cudaStream_t>(stream), tokens ? tokens : e->x,
                       reinterpret_cast<const long long*>(flag), text_mask, template_mask, context_mask, 0, prompt_out);
+}
+
+int uvlt_head(uvlt_handle e, const float* search_tokens, const float* prompt, const int64_t* flag, int32_t B,
+              uvlt_outputs* out, void* stream) {
+  if (!e) { set_error("null handle"); return 1; }
+  if (check_batch(e, B)) return 1;
+  if (!prompt || !flag) { set_error("uvlt_head: prompt and flag are required (test branch of the head)"); return 1; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan* p = get_plan(e, B, false);
+  if (!p) return 1;
+  e->launch_count = 0;
+  if (search_tokens) {  // [B, Nx, D] -> the search rows of the engine's token stream
+    const size_t row_bytes = static_cast<size_t>(e->Nx) * e->D * sizeof(float);
+    ENG_CUDA(cudaMemcpy2DAsync(e->x + static_cast<size_t>(1 + e->Nz) * e->D, static_cast<size_t>(e->N) * e->D * sizeof(float),
+                               search_tokens, row_bytes, row_bytes, B, cudaMemcpyDeviceToDevice, s));
+  }
+  ENG_CUDA(cudaMemcpyAsync(e->flag_d, flag, static_cast<size_t>(B) * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+  ENG_CUDA(cudaMemcpyAsync(e->prompt_d, prompt, static_cast<size_t>(B) * 3 * e->D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (run_head(e, p, s, false)) return 1;
+  e->last_B = B;
+  e->last_cont_cols = e->cfg.softmax_one ? 3 : 2;
+  fill_outputs(e, B, out, false);
+  return 0;
 }
 
 int uvlt_track_decode(uvlt_handle e, const double* window, int32_t has_cont, float* max_score, float* snapshot,

@@ -484,13 +484,17 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   pdl_trigger();
   if (threadIdx.x == 0) TRACE_PT(0x102);
 
-  // tile t -> (group, n tile, m pair): m fastest, so the clusters running at the same time share W tiles in L2
+  // tile t -> (group, m pair, n tile): n fastest, so the ~74 clusters running at the same time cover a BAND of M with
+  // every N tile of it: each A tile is fetched from HBM once and re-read from L2 by the clusters of the other N tiles,
+  // and the whole weight matrix (<= 4.7 MB) stays L2 resident.  With m fastest (round 1) one wave streamed the full A
+  // operand per N tile: fc2 at M = 17696 read its 108.7 MB A operand three times (ncu dram__bytes_read 318.6 MB against
+  // 167.8 MB algorithmic, profiles/r01_final_b32_gemm_full.md).
   auto tile_coords = [&](int t, int& g, int& m0, int& n0) {
     g = t / tiles_per_group;
     const int r = t - g * tiles_per_group;
-    const int nt = r / m_pairs;
-    m0 = ((r - nt * m_pairs) * 2 + static_cast<int>(crank)) * GEMM_BM;
-    n0 = nt * BN;
+    const int mp = r / n_tiles;
+    m0 = (mp * 2 + static_cast<int>(crank)) * GEMM_BM;
+    n0 = (r - mp * n_tiles) * BN;
   };
 
   if (warp == 0) {

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <set>
 
 namespace uvlt {
 
@@ -76,11 +77,15 @@ static int g_attn_poly = [] {
   return (e && e[0] == '1') ? 1 : 0;
 }();
 
+// cudaFuncSetAttribute applies to the CURRENT device: the opt-in is tracked per device ordinal, so a process that creates
+// engines on several GPUs gets it on each of them (one process per GPU remains the supported layout, dp.py).
 int init_kernel_attributes() {
-  static int status = -1;
+  static std::set<int> done;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
-  if (status == 0) return 0;
+  int cur_dev = 0;
+  UVLT_CUDA_OK(cudaGetDevice(&cur_dev));
+  if (done.count(cur_dev)) return 0;
 #define UVLT_GEMM_ATTR(BN, EPI)                                                                                     \
   UVLT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     GemmSmem<BN>::total(GemmSmem<BN>::STAGES_2CTA)));                                 \
@@ -111,7 +116,7 @@ int init_kernel_attributes() {
     UVLT_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     g_num_sms = sms > 1 ? sms : 148;
   }
-  status = 0;
+  done.insert(cur_dev);
   return 0;
 }
 

@@ -44,31 +44,51 @@ def init_process_group(backend: str | None = None):
 
 
 def gather_trajectories(local, n_sequences: int | None = None):
-    """All-gather per-rank trajectories [S_local, T, C] into [S_total, T, C] on every rank, in rank order.
+    """All-gather per-rank trajectories [S_local, T, C] into [S_total, T, C] on every rank, in rank order: the ONE
+    collective of a run.
 
-    Ranks may own different numbers of sequences (shard_range); blocks are padded to the largest shard for the
-    collective and trimmed afterwards.  With one process this is the identity."""
+    Ranks may own different numbers of sequences; the shard sizes follow from ``shard_range`` (pass ``n_sequences`` = the
+    global sequence count), so no second collective is needed to exchange them.  Blocks are padded to the largest shard
+    for the collective and trimmed afterwards.  With one process this is the identity."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local
-    world = dist.get_world_size()
-    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
-    counts[dist.get_rank()] = local.shape[0]
-    dist.all_reduce(counts)
-    counts = counts.tolist()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if n_sequences is None:
+        n_sequences = local.shape[0] * world  # equal shards
+    counts = [shard_range(n_sequences, r, world) for r in range(world)]
+    counts = [b - a for a, b in counts]
+    if counts[rank] != local.shape[0]:
+        raise RuntimeError(f"rank {rank} holds {local.shape[0]} sequences, shard_range gives {counts[rank]} of {n_sequences}")
     smax = max(counts)
-    send = local.new_zeros((smax,) + tuple(local.shape[1:]))
-    send[: local.shape[0]] = local
-    recv = local.new_empty((world * smax,) + tuple(local.shape[1:]))
+    if local.shape[0] == smax:
+        send = local.contiguous()
+    else:
+        send = local.new_zeros((smax,) + tuple(local.shape[1:]))
+        send[: local.shape[0]] = local
     if dist.get_backend() == "nccl":
-        dist.all_gather_into_tensor(recv, send.contiguous())
+        recv = local.new_empty((world * smax,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(recv, send)
     else:
         parts = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(parts, send.contiguous())
+        dist.all_gather(parts, send)
         recv = torch.cat(parts, dim=0)
-    out = torch.cat([recv[r * smax: r * smax + counts[r]] for r in range(world)], dim=0)
-    if n_sequences is not None and out.shape[0] != n_sequences:
-        raise RuntimeError(f"gathered {out.shape[0]} sequences, expected {n_sequences}")
-    return out
+    if all(c == smax for c in counts):
+        return recv
+    return torch.cat([recv[r * smax: r * smax + counts[r]] for r in range(world)], dim=0)
+
+
+def warmup_gather(like):
+    """One all-gather of the same shape / dtype as the run's final ``gather_trajectories`` call, issued BEFORE a timed
+    region: NCCL builds its communicator, channels and kernels lazily at the first collective (several milliseconds),
+    which is set-up cost of the process, not of the run."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    gather_trajectories(torch.zeros_like(like))
+    if like.is_cuda:
+        torch.cuda.synchronize()

@@ -183,6 +183,21 @@ class Engine:
         res["_text_mask"] = mask
         return res
 
+    def head(self, search, prompt, flag, clone=True):
+        """ModalityAdaptiveBoxHead.forward, test branch (modality_adaptive_box_head.py:62-94,140-148) on backbone features
+        ``search`` [B, Nx, D] (None: the token stream the last backbone call left in the engine)."""
+        prompt = self._f32(prompt)
+        B = prompt.shape[0]
+        fl = self._i64(flag).reshape(-1)
+        srch = None if search is None else self._f32(search)
+        if srch is not None and tuple(srch.shape) != (B, self.dims.nx, self.dims.embed_dim):
+            raise ValueError("search tokens must be [B, Nx, D]")
+        out = _cabi.UvltOutputs()
+        _cabi.check(self.lib.uvlt_head(self.h, _cabi.ptr(srch), _cabi.ptr(prompt), _cabi.ptr(fl), B, C.byref(out),
+                                       _cabi.current_stream()), "uvlt_head")
+        res = self._outputs(out, head=True, clone=clone)
+        return {k: res[k] for k in ("cls_score", "cls_score_test", "bbox_map", "pred_boxes", "cont_score", "prompts")}
+
     def backbone(self, template, search, text, flag, want_logits=False, clone=True):
         """ModalityUnifiedFeatureExtractor.forward (modality_unified_feature_extractor.py:52-77)."""
         B = search.shape[0]

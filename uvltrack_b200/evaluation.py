@@ -164,8 +164,12 @@ def run_dataset_batched(dataset: Seq[Sequence], tracker: Tracker, batch: int, ra
     todo.sort(key=len, reverse=True)  # similar lengths share a batch
     done = {}
     bt = None
-    for i in range(0, len(todo), batch):
-        group: List[Sequence] = todo[i:i + batch]
+
+    def run_group(group: List[Sequence]):
+        """One batch of sequences through the BatchTracker.  Returns one output dict per sequence, None for a sequence
+        that failed (unreadable frame, 'Too small bounding box.'): like the reference's run_sequence (running.py:124-128)
+        a failure costs that sequence only -- the lane is frozen and the sequences sharing the batch run to their end."""
+        nonlocal bt
         pad = batch - len(group)
         seqs = group + [group[-1]] * pad  # a short last group is padded with a copy whose rows are dropped
         if bt is None:
@@ -174,16 +178,51 @@ def run_dataset_batched(dataset: Seq[Sequence], tracker: Tracker, batch: int, ra
         infos = [dict(s.init_info(), language=s.language, seq_name=s.name) for s in seqs]
         bt.initialize([read_image(s.frames[0]) for s in seqs], infos)
         outs = [{"target_bbox": [s.init_info()["init_bbox"]], "time": [time.time() - t0]} for s in group]
+        dead = [None] * len(seqs)
+        last = [None] * len(seqs)
         n_max = max(len(s) for s in group)
         for t in range(1, n_max):
             t0 = time.time()
-            res = bt.track([read_image(s.frames[min(t, len(s) - 1)]) for s in seqs])
+            frames = []
+            for b, s in enumerate(seqs):
+                try:
+                    if dead[b] is None:
+                        last[b] = read_image(s.frames[min(t, len(s) - 1)])
+                except Exception as e:  # an unreadable frame ends this sequence only
+                    dead[b] = f"{type(e).__name__}: {e}"
+                if last[b] is None:
+                    last[b] = read_image(s.frames[0])
+                frames.append(last[b])
+            res = bt.track(frames, raise_on_failure=False)
             dt = (time.time() - t0) / len(group)
             for b, s in enumerate(group):
-                if t < len(s):
+                if dead[b] is None and res[b].get("failed"):
+                    dead[b] = res[b].get("error", "failed")
+                if dead[b] is None and t < len(s):
                     outs[b]["target_bbox"].append(res[b]["target_bbox"])
                     outs[b]["time"].append(dt)
+        for b, s in enumerate(group):
+            if dead[b] is not None:
+                print(f"{s.name}: {dead[b]}")
+                outs[b] = None
+        return outs
+
+    for i in range(0, len(todo), batch):
+        group: List[Sequence] = todo[i:i + batch]
+        try:
+            outs = run_group(group)
+        except Exception as e:  # e.g. a first frame that cannot be read: isolate the culprit by running the group one by one
+            print(e)
+            outs = []
+            for s in group:
+                try:
+                    outs.extend(run_group([s]))
+                except Exception as e1:
+                    print(f"{s.name}: {e1}")
+                    outs.append(None)
         for s, o in zip(group, outs):
+            if o is None:
+                continue  # skipped, like a failed sequence of the reference: no result file, the rest of the shard goes on
             save_tracker_output(tracker.results_dir, subdir, s.name, o)
             done[s.name] = np.array(o["target_bbox"], dtype=np.float64)
     return done

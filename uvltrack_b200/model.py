@@ -39,6 +39,21 @@ class ModalityAdaptiveBoxHead:
         self.softmax_one = cfg.MODEL.HEAD.SOFTMAX_ONE
         self.engine = None
 
+    def forward(self, out_dict, test=False):
+        """ModalityAdaptiveBoxHead.forward (modality_adaptive_box_head.py:62-94): updates and returns ``out_dict`` with
+        cls_score / cls_score_test / bbox_map / pred_boxes / cont_score / prompts.  The test-time branch: the prompt is
+        in ``out_dict['prompt']`` as UVLTrack.forward_test injects it (uvltrack.py:43); without a prompt the reference
+        head derives one from the batch's own template / context masks, which is what MODELS['uvltrack'].forward does."""
+        if self.engine is None:
+            raise RuntimeError("head is not bound to an engine: build it through MODELS['uvltrack'](cfg)")
+        if out_dict.get("prompt") is None:
+            raise NotImplementedError("head.forward without out_dict['prompt'] is the training branch: call "
+                                      "MODELS['uvltrack'](cfg).forward(template, search, text, template_mask, context_mask, flag)")
+        out_dict.update(self.engine.head(out_dict["search"], out_dict["prompt"], out_dict["flag"]))
+        return out_dict
+
+    __call__ = forward
+
     def forward_prompt(self, out_dict):
         if self.engine is None:
             raise RuntimeError("head is not bound to an engine: build it through MODELS['uvltrack'](cfg)")

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 import os
+import time
 import unicodedata
 
 import numpy as np
@@ -167,6 +168,7 @@ class BatchTracker:
         self.tokenizer = None
         self.frame_id = 0
         self.state = [None] * self.B
+        self.failed = [None] * self.B  # per-sequence failure message (frozen lane), reset by initialize()
         self.max_score = [0.0] * self.B
         self.pred_box_net = [None] * self.B
         d, dev = self.dims, "cuda"
@@ -191,6 +193,12 @@ class BatchTracker:
         self._fast = None   # raw pointers of the per-frame engine call, bound per frame size
         self._pool = None
         self.h2d_bytes = 0  # bytes of raw frames uploaded by track() so far (search windows only)
+        # host wall-clock seconds spent per phase of track() so far (bench.py reports them as e2e_phases):
+        #   stage_h2d  pageable frame -> pinned staging copies + enqueueing the async window uploads
+        #   engine     the blocking engine call: H2D completion, crop/resize, forward, merge, box update, D2H, sync
+        #   host_post  per-sequence bookkeeping of the result rows
+        #   prompt     prompt updates (every UPDATE_INTERVAL frames)
+        self.phase_s = {"stage_h2d": 0.0, "engine": 0.0, "host_post": 0.0, "prompt": 0.0}
         self.skip_text = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -228,18 +236,50 @@ class BatchTracker:
         out = self.network.forward(template, ground, text, tm, cm, torch.tensor([[1]]).cuda())
         return pp.grounding_box(out["pred_boxes"][0, 0].cpu().numpy(), h, w)
 
+    def _init_crops_device(self, images, boxes):
+        """Template and context crops of every sequence on the device: the B first frames go up once,
+        then per crop kind one crop_resize launch (sample_target, bit-exact with cv2.resize), one normalisation launch
+        (Preprocessor_wo_mask) and one anno2mask launch for the whole batch.  Only the four numbers of the normalised
+        target box per crop are computed on the host (processing_utils.py:206: Python floats -> fp32 tensor)."""
+        import torch
+
+        from . import _cabi
+
+        lib, d, B = self.engine.lib, self.dims, self.B
+        H, W = images[0].shape[:2]
+        frames = torch.from_numpy(np.ascontiguousarray(np.stack(images))).cuda()
+        state = torch.tensor([[float(v) for v in bb] for bb in boxes], dtype=torch.float64, device="cuda")
+        stream = _cabi.current_stream()
+        outs = []
+        for factor, size in ((self.params.template_factor, self.params.template_size),
+                             (self.params.search_factor, self.params.search_size)):
+            crops = torch.empty(B, size, size, 3, dtype=torch.uint8, device="cuda")
+            rf = torch.empty(B, dtype=torch.float64, device="cuda")
+            _cabi.check(lib.uvlt_op_crop_resize(frames.data_ptr(), H, W, state.data_ptr(), float(factor), size,
+                                                crops.data_ptr(), rf.data_ptr(), B, stream), "uvlt_op_crop_resize")
+            img = torch.empty(B, 3, size, size, dtype=torch.float32, device="cuda")
+            _cabi.check(lib.uvlt_op_normalize_u8(crops.data_ptr(), img.data_ptr(), size, B, stream), "uvlt_op_normalize_u8")
+            nb = np.zeros((B, 4), dtype=np.float32)
+            for b, (x, y, w, h) in enumerate(boxes):
+                crop_sz = math.ceil(math.sqrt(float(w) * float(h)) * factor)
+                if crop_sz < 1:
+                    raise Exception("Too small bounding box.")  # lib/train/data/processing_utils.py:180
+                nb[b] = [0.5 - w / crop_sz / 2, 0.5 - h / crop_sz / 2, w / crop_sz, h / crop_sz]
+            d_nb = torch.from_numpy(nb).cuda()
+            mask = torch.empty(B, (size // 16) ** 2, dtype=torch.uint8, device="cuda")
+            _cabi.check(lib.uvlt_op_anno2mask(d_nb.data_ptr(), size // 16, mask.data_ptr(), B, stream), "uvlt_op_anno2mask")
+            outs += [img, mask]
+        return outs  # template, template_mask, context, context_mask
+
     def initialize(self, images, infos):
         """lib/test/tracker/uvltrack.py:70-104 for every sequence of the batch."""
         import torch
 
         d, mode = self.dims, self.cfg.TEST.MODE
-        ctx = torch.zeros(self.B, 3, d.search_size, d.search_size)
-        tmpl = torch.zeros(self.B, 3, d.template_size, d.template_size)
-        ctx_mask = np.zeros((self.B, d.nx), dtype=np.uint8)
-        tm_mask = np.zeros((self.B, d.nz), dtype=np.uint8)
         ids_all = np.zeros((self.B, d.text_len), dtype=np.int64)
         mask_all = np.zeros((self.B, d.text_len), dtype=np.float32)
         flags = np.zeros(self.B, dtype=np.int64)
+        boxes = []
         for b, (image, info) in enumerate(zip(images, infos)):
             if mode == "NL":
                 ids, mask = self._tokens_for(info)
@@ -254,22 +294,37 @@ class BatchTracker:
                 init_bbox = list(info["init_bbox"])
                 flags[b] = 0
             ids_all[b], mask_all[b] = ids, mask
-            z_patch, _, z_box = pp.sample_target(image, init_bbox, self.params.template_factor, self.params.template_size)
-            tm_mask[b] = pp.anno2mask(z_box.reshape(1, 4), d.template_size // 16)[0]
-            tmpl[b] = torch.from_numpy(pp.normalize_image(z_patch))[0]
-            y_patch, _, y_box = pp.sample_target(image, init_bbox, self.params.search_factor, self.params.search_size)
-            ctx[b] = torch.from_numpy(pp.normalize_image(y_patch))[0]
-            ctx_mask[b] = pp.anno2mask(y_box.reshape(1, 4), d.search_size // 16)[0]
+            boxes.append([float(v) for v in init_bbox])
             self.state[b] = init_bbox
             self.max_score[b] = 0.0
             self.pred_box_net[b] = None
-        self.template.copy_(tmpl)
+            self.failed[b] = None
+        uniform = len({im.shape for im in images}) == 1 and images[0].dtype == np.uint8 and images[0].ndim == 3
+        if self.device_preprocess and uniform:
+            tmpl, tm_mask, ctx, ctx_mask = self._init_crops_device(images, boxes)
+            self.template.copy_(tmpl)
+            self.template_mask.copy_(tm_mask)
+        else:
+            # the reference's host path (OpenCV), one sequence at a time: mixed frame sizes / device_preprocess off
+            ctx = torch.zeros(self.B, 3, d.search_size, d.search_size)
+            tmpl = torch.zeros(self.B, 3, d.template_size, d.template_size)
+            ctx_mask = np.zeros((self.B, d.nx), dtype=np.uint8)
+            tm_mask = np.zeros((self.B, d.nz), dtype=np.uint8)
+            for b, image in enumerate(images):
+                z_patch, _, z_box = pp.sample_target(image, boxes[b], self.params.template_factor, self.params.template_size)
+                tm_mask[b] = pp.anno2mask(z_box.reshape(1, 4), d.template_size // 16)[0]
+                tmpl[b] = torch.from_numpy(pp.normalize_image(z_patch))[0]
+                y_patch, _, y_box = pp.sample_target(image, boxes[b], self.params.search_factor, self.params.search_size)
+                ctx[b] = torch.from_numpy(pp.normalize_image(y_patch))[0]
+                ctx_mask[b] = pp.anno2mask(y_box.reshape(1, 4), d.search_size // 16)[0]
+            self.template.copy_(tmpl)
+            self.template_mask.copy_(torch.from_numpy(tm_mask))
+            ctx, ctx_mask = ctx.cuda(), torch.from_numpy(ctx_mask).cuda()
         self.ids.copy_(torch.from_numpy(ids_all))
         self.text_mask.copy_(torch.from_numpy(mask_all))
         self.flag.copy_(torch.from_numpy(flags))
-        self.template_mask.copy_(torch.from_numpy(tm_mask))
         self.max_score_dev.zero_()
-        self.state_dev.copy_(torch.tensor([[float(v) for v in st] for st in self.state], dtype=torch.float64))
+        self.state_dev.copy_(torch.tensor(boxes, dtype=torch.float64))
         self.skip_text = bool((flags == 0).all())
         text = NestedTensor(self.ids, self.text_mask)
         # the language branch before the first fusion layer depends only on the (constant) text: run it once here and
@@ -278,8 +333,7 @@ class BatchTracker:
         if self.text_cached:
             self.engine.text_encode(text, self.flag)
             self.engine._text_owner = self  # the cache lives in the engine: another tracker on it may overwrite it
-        self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx.cuda(), text, self.template_mask,
-                                                           torch.from_numpy(ctx_mask).cuda(), self.flag))
+        self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx, text, self.template_mask, ctx_mask, self.flag))
         self.frame_id = 0
         torch.cuda.synchronize()
 
@@ -294,13 +348,20 @@ class BatchTracker:
             "snapshot": self.snapshot.data_ptr(), "out10": self.out10.data_ptr(),
         }
 
-    def track(self, images):
-        """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch."""
+    def track(self, images, raise_on_failure: bool = True):
+        """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch.
+
+        A sequence whose crop side drops below one pixel fails the way the reference does ('Too small bounding box.',
+        processing_utils.py:180).  With ``raise_on_failure`` (default, the single-tracker semantics) that raises; the
+        batched evaluation scheduler passes False: the failed lane is frozen (its state no longer changes, its result
+        rows carry ``failed=True``) and the healthy sequences sharing the batch keep going."""
         import torch
 
         self.frame_id += 1
         S = self.params.search_size
         results, update = [], []
+        t_start = time.perf_counter()
+        t_staged = t_engine = None
         if self.text_cached and getattr(self.engine, "_text_owner", None) is not self:
             self.engine.text_encode(NestedTensor(self.ids, self.text_mask), self.flag)
             self.engine._text_owner = self
@@ -349,10 +410,12 @@ class BatchTracker:
                     self._pool = ThreadPoolExecutor(max_workers=min(8, self.B),
                                                     initializer=lambda: torch.cuda.set_device(dev))
                 self.h2d_bytes += sum(self._pool.map(stage, range(self.B)))
+            t_staged = time.perf_counter()
             rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
                                                  f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
                                                  (2 if self.skip_text else 0) | (4 if self.text_cached else 0),
                                                  int(self.has_cont), f["max_score"], f["snapshot"], f["out10"], stream)
+            t_engine = time.perf_counter()
             if rc:
                 from . import _cabi
 
@@ -360,8 +423,12 @@ class BatchTracker:
             rows = []
             for b in range(self.B):
                 row = self.out10_np[b]
-                if row[9] < 0:
-                    raise Exception("Too small bounding box.")  # lib/train/data/processing_utils.py:180
+                if row[9] < 0:  # crop side < 1 px: the device left this sequence's state untouched
+                    if raise_on_failure:
+                        raise Exception("Too small bounding box.")  # lib/train/data/processing_utils.py:180
+                    self.failed[b] = "Too small bounding box."
+                    rows.append((np.zeros(4, dtype=np.float32), 0.0))
+                    continue
                 self.state[b] = row[:4].tolist()
                 self.out_np[b, :4], self.out_np[b, 4], self.out_np[b, 5] = row[4:8], row[8], row[9]
                 rows.append((row[4:8].astype(np.float32), float(np.float32(row[8]))))
@@ -369,7 +436,13 @@ class BatchTracker:
             # ---- the reference's host pre/post-processing around the device forward ----
             rf = [0.0] * self.B
             for b, image in enumerate(images):
-                crop, rf[b], _ = pp.sample_target(image, self.state[b], self.params.search_factor, S)
+                try:
+                    crop, rf[b], _ = pp.sample_target(image, self.state[b], self.params.search_factor, S)
+                except Exception as e:
+                    if raise_on_failure or "Too small" not in str(e):
+                        raise
+                    self.failed[b] = str(e)
+                    crop, rf[b] = np.zeros((S, S, 3), dtype=np.uint8), 0.0
                 self.crops_np[b] = crop
             self.engine.track_frame_host(self.crops, self.template, self.ids, self.text_mask, self.prompt, self.flag,
                                          self.window_dev, self.out, self.B, has_cont=self.has_cont,
@@ -379,6 +452,9 @@ class BatchTracker:
             for b, image in enumerate(images):
                 H, W = image.shape[:2]
                 row = self.out_np[b]
+                if self.failed[b]:
+                    rows.append((np.zeros(4, dtype=np.float32), 0.0))
+                    continue
                 pred_box_net = row[:4].copy()
                 pred_box = (pred_box_net * np.float32(S) / np.float32(rf[b])).tolist()
                 self.state[b] = pp.clip_box(pp.map_box_back(self.state[b], pred_box, rf[b], S), H, W, margin=10)
@@ -387,12 +463,16 @@ class BatchTracker:
                 self.state_dev.copy_(torch.tensor(self.state, dtype=torch.float64))
         for b in range(self.B):
             pred_box_net, score = rows[b]
+            if self.failed[b]:
+                results.append({"target_bbox": self.state[b], "score": 0.0, "failed": True, "error": self.failed[b]})
+                continue
             if score > self.max_score[b] and self.has_cont:
                 self.pred_box_net[b] = pred_box_net
                 self.max_score[b] = score
             if self.frame_id % self.update_interval == 0 and self.has_cont and self.max_score[b] > self.threshold:
                 update.append(b)
             results.append({"target_bbox": self.state[b], "score": score})
+        t_post = time.perf_counter()
         if update:
             cm = np.zeros((self.B, self.dims.nx), dtype=np.uint8)
             for b in update:
@@ -405,6 +485,15 @@ class BatchTracker:
             self.max_score_dev[sel] = 0
             for b in update:
                 self.max_score[b] = 0.0
+        t_end = time.perf_counter()
+        ph = self.phase_s
+        if t_staged is not None:
+            ph["stage_h2d"] += t_staged - t_start
+            ph["engine"] += t_engine - t_staged
+            ph["host_post"] += t_post - t_engine
+        else:
+            ph["engine"] += t_post - t_start
+        ph["prompt"] += t_end - t_post
         return results
 
 

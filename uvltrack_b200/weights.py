@@ -128,8 +128,14 @@ def sincos_pos_embed(dim: int, grid_size: int) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def synthetic_state_dict(dims: ModelDims, seed: int = 0, cls_sharpen: float = 4.0) -> "OrderedDict[str, np.ndarray]":
-    """Reference-format ``state_dict`` (fp32 numpy) for every parameter/buffer reachable from the hot path."""
+def synthetic_state_dict(dims: ModelDims, seed: int = 0, cls_sharpen: float = 4.0,
+                         reg_gain: float = 2.0) -> "OrderedDict[str, np.ndarray]":
+    """Reference-format ``state_dict`` (fp32 numpy) for every parameter/buffer reachable from the hot path.
+
+    ``cls_sharpen``: gain on the last 1x1 conv of the classification tower (a peaked score map).
+    ``reg_gain``: gain on the 3x3 convs of the offset / size towers relative to nn.Conv2d's default initialisation (the cls
+    tower always gets 2).  The golden files were generated with 2 (x16 over the four layers); 1 = the reference's own
+    initialisation scale, used by the +-1 px box tests."""
     rng = np.random.default_rng(seed)
     D, Hd = dims.embed_dim, dims.mlp_hidden
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
@@ -196,7 +202,8 @@ def synthetic_state_dict(dims: ModelDims, seed: int = 0, cls_sharpen: float = 4.
         for j in range(4):
             cin, cout = chans[j], chans[j + 1]
             bound = 1.0 / math.sqrt(cin * 9)
-            sd[f"{h}.{tower}.{j}.0.weight"] = rng.uniform(-bound, bound, (cout, cin, 3, 3)).astype(np.float32) * 2.0
+            gain = 2.0 if tower == "conv_cls" else reg_gain
+            sd[f"{h}.{tower}.{j}.0.weight"] = rng.uniform(-bound, bound, (cout, cin, 3, 3)).astype(np.float32) * np.float32(gain)
             sd[f"{h}.{tower}.{j}.0.bias"] = rng.uniform(-bound, bound, (cout,)).astype(np.float32)
             sd[f"{h}.{tower}.{j}.1.weight"] = rng.uniform(0.5, 1.5, (cout,)).astype(np.float32)
             sd[f"{h}.{tower}.{j}.1.bias"] = normal((cout,), 0.1) + np.float32(0.1)
