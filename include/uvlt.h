@@ -101,6 +101,9 @@ typedef struct uvlt_outputs {
                               (modality_unified_feature_extractor.py:47), so the BERT branch and the text rows are
                               not evaluated; `tokens` text rows are then undefined.  Image-side results are identical. */
 
+#define UVLT_FRAME_SLOT1 8 /* uvlt_track_frame_image_host: crop from frame-staging slot 1 (filled with
+                              uvlt_upload_frames_slot) instead of slot 0 */
+
 #define UVLT_TEXT_CACHED 4 /* the text rows entering the first fusion layer were computed by uvlt_text_encode for these
                               sequences (ids / text_mask are constant per sequence): the BERT embedding and the
                               BERT-only layers are not re-run, their rows are restored from the cache.  Bit-identical. */
@@ -189,6 +192,15 @@ UVLT_API int uvlt_track_frame_image_host(uvlt_handle h, const uint8_t* frames_ho
  * the DMA, piece by piece.  Enqueued on `stream`; no synchronisation (except when the buffer has to grow). */
 UVLT_API int uvlt_upload_frames(uvlt_handle h, const uint8_t* host, int64_t dst_offset, int64_t nbytes,
                                 int64_t total_bytes, void* stream);
+
+/* Double-buffered variant: the engine keeps TWO frame-staging buffers.  While a step crops from one slot the caller
+ * uploads the next step's frames into the other one on a SECOND stream (and makes the step's stream wait on an event
+ * recorded after the upload), then passes UVLT_FRAME_SLOT1 / no flag to uvlt_track_frame_image_host accordingly: the H2D
+ * copy of step t+1 overlaps the forward of step t.  The three upload entry points only enqueue copies (and grow the
+ * buffer under a mutex): they are the one part of the ABI that may be called from other host threads than the handle's
+ * owner. */
+UVLT_API int uvlt_upload_frames_slot(uvlt_handle h, const uint8_t* host, int64_t dst_offset, int64_t nbytes,
+                                     int64_t total_bytes, int32_t slot, void* stream);
 
 /* Same, for a sub-rectangle: `rows` rows of `width_bytes` from `host` (row pitch src_pitch) to byte offset dst_offset of
  * the staging buffer with row pitch dst_pitch (= frame_w * 3).  sample_target only reads the search window

@@ -82,7 +82,7 @@ class _FakeBatchTracker:
         self.failed = [None] * self.B
         self.n = 0
 
-    def track(self, images, raise_on_failure=True):
+    def track(self, images, raise_on_failure=True, next_images=None):
         self.n += 1
         out = []
         for b in range(self.B):

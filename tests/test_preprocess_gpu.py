@@ -116,3 +116,35 @@ def test_window_upload_never_reads_stale_pixels():
         for b in range(B):
             assert rd[b]["target_bbox"] == rh[b]["target_bbox"], (t, b, rd[b], rh[b])
     assert 0 < uploaded < n * B * 480 * 640 * 3  # windows, not whole frames
+
+
+def test_prefetched_frames_give_identical_tracks():
+    """track(images, next_images=...) stages and uploads the next step's frames into the engine's second staging buffer
+    while the current step runs; the boxes must be identical to the plain one-frame-at-a-time path, including when the
+    caller breaks its promise and passes different frames than it announced."""
+    z, x, B, n = 128, 256, 2, 8
+    dims = ModelDims.base(z, x)
+    cfg = config.baseline_cfg("base", z, x, mode="BBOX")
+    params = config.parameters(cfg)
+    params.state_dict = synthetic_state_dict(dims, seed=0)
+    seqs = [synthetic_sequence(n + 1, seed=70 + b) for b in range(B)]
+    infos = [{"init_bbox": s[1][0]} for s in seqs]
+    tracks = {}
+    for mode in ("plain", "prefetch", "broken_promise"):
+        bt = BatchTracker(params, batch=B)
+        bt.initialize([s[0][0] for s in seqs], infos)
+        out = []
+        for t in range(1, n + 1):
+            cur = [s[0][t] for s in seqs]
+            nxt = [s[0][t + 1] for s in seqs] if t < n else None
+            if mode == "plain":
+                res = bt.track(cur)
+            elif mode == "prefetch":
+                res = bt.track(cur, next_images=nxt)
+            else:  # announce frame t+1 of the OTHER sequence order: the tracker must notice and stage `cur` itself
+                res = bt.track(cur, next_images=nxt[::-1] if nxt else None)
+            out.append([r["target_bbox"] for r in res])
+        tracks[mode] = np.array(out)
+        bt.engine.close()
+    assert np.array_equal(tracks["plain"], tracks["prefetch"])
+    assert np.array_equal(tracks["plain"], tracks["broken_promise"])

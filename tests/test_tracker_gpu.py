@@ -72,18 +72,21 @@ def test_track_matches_oracle_teacher_forced(mode):
             O.softmax(ref["cont_score"][0])[:, 0].astype(np.float64)
         top2 = np.sort(merged)[-2:]
         row = bt.out_np[0]
-        if top2[1] - top2[0] > 2e-2:
-            assert int(row[5]) == j, (t, row, j)
-            err_px = float(np.abs(row[:4] - box).max()) * x
-            errs.append(err_px)
-            assert err_px < BOX_TOL_PX, (t, err_px)
+        # +-1 px on EVERY frame: the box the tracker regressed at the cell it selected vs the oracle's box at that cell
+        k = int(row[5])
+        err_px = float(np.abs(row[:4] - ref["bbox_map"][0][k]).max()) * x
+        errs.append(err_px)
+        assert err_px < BOX_TOL_PX, (t, err_px)
+        # frames whose oracle top-1 / top-2 margin is outside the bf16 noise of the merged score: same cell, same state
+        if top2[1] - top2[0] > 2e-2 * max(top2[1], 0.05):
+            assert k == j, (t, row, j)
             ref_state = O.clip_box(O.map_box_back(state_before, (box * np.float32(x) / np.float32(rf)).tolist(), rf, x),
                                    frames[t].shape[0], frames[t].shape[1], margin=10)
             assert np.abs(np.array(out["target_bbox"]) - np.array(ref_state)).max() < BOX_TOL_PX / rf + 1e-3
             checked += 1
     # the trajectory is the tracker's own (teacher forcing only feeds the oracle), so how many frames have a decisive
-    # top-1 / top-2 margin depends on it; every decisive frame must match within 1 px
-    print(f"[{mode}] decisive frames {checked}/{n}, box error px: max {max(errs):.3f} mean {np.mean(errs):.3f}")
+    # top-1 / top-2 margin depends on it
+    print(f"[{mode}] decisive frames {checked}/{n}, box error px over all {n} frames: max {max(errs):.3f} mean {np.mean(errs):.3f}")
     assert checked >= n // 2, f"only {checked} of {n} frames had a decisive margin"
     assert bt.frame_id == n
 

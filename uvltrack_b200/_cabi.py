@@ -44,6 +44,7 @@ class UvltOutputs(C.Structure):
 WANT_LOGITS = 1
 SKIP_TEXT = 2
 TEXT_CACHED = 4
+FRAME_SLOT1 = 8
 
 _P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/uvlt.h declares (tests/test_cabi_symbols.py checks)
@@ -70,6 +71,7 @@ SIGNATURES = {
     "uvlt_op_normalize_u8": (c_int, [_P, _P, c_int32, c_int32, _P]),
     "uvlt_text_encode": (c_int, [_P, _P, _P, _P, c_int32, _P]),
     "uvlt_upload_frames": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P]),
+    "uvlt_upload_frames_slot": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int32, _P]),
     "uvlt_upload_frames_2d": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P]),
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

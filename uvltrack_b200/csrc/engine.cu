@@ -119,8 +119,10 @@ struct uvlt_engine {
   int* snap_flag = nullptr;
   uint8_t* u8_stage = nullptr;
   // device-resident tracker step (track.cuh)
-  uint8_t* frame_stage = nullptr;  // [B, H, W, 3] staging of the raw frames, grown on demand
-  size_t frame_stage_bytes = 0;
+  // [B, H, W, 3] staging of the raw frames, grown on demand.  Two slots: while a step crops from one, the caller may
+  // upload the next step's frames into the other on a second stream (UVLT_FRAME_SLOT1, uvlt_upload_frames_slot)
+  uint8_t* frame_stage_[2] = {nullptr, nullptr};
+  size_t frame_stage_bytes_[2] = {0, 0};
   std::mutex stage_mu;
   double *rf_d = nullptr, *out10_d = nullptr;
 
@@ -791,16 +793,16 @@ int run_core(uvlt_engine* e, Plan* p, cudaStream_t s, bool want_logits, bool wit
   return 0;
 }
 
-int grow_frame_stage(uvlt_engine* e, size_t bytes, cudaStream_t s) {
-  std::lock_guard<std::mutex> lk(e->stage_mu);  // uvlt_upload_frames may be called from several host threads
-  if (bytes <= e->frame_stage_bytes) return 0;
+int grow_frame_stage(uvlt_engine* e, size_t bytes, cudaStream_t s, int slot = 0) {
+  std::lock_guard<std::mutex> lk(e->stage_mu);  // the upload entry points may be called from several host threads
+  if (bytes <= e->frame_stage_bytes_[slot]) return 0;
   // first frame of a sequence (or a larger video): grow the staging buffer
   ENG_CUDA(cudaStreamSynchronize(s));
-  if (e->frame_stage) cudaFree(e->frame_stage);
-  e->frame_stage = nullptr;
-  e->frame_stage_bytes = 0;
-  ENG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->frame_stage), bytes));
-  e->frame_stage_bytes = bytes;
+  if (e->frame_stage_[slot]) cudaFree(e->frame_stage_[slot]);
+  e->frame_stage_[slot] = nullptr;
+  e->frame_stage_bytes_[slot] = 0;
+  ENG_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->frame_stage_[slot]), bytes));
+  e->frame_stage_bytes_[slot] = bytes;
   return 0;
 }
 
@@ -928,7 +930,8 @@ void uvlt_destroy(uvlt_handle e) {
     for (auto& g : kv.second->graph)
       if (g) cudaGraphExecDestroy(g);
   for (void* p : e->allocs) cudaFree(p);
-  if (e->frame_stage) cudaFree(e->frame_stage);
+  for (int i = 0; i < 2; ++i)
+    if (e->frame_stage_[i]) cudaFree(e->frame_stage_[i]);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->cap) cudaStreamDestroy(e->cap);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -1162,14 +1165,15 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
   if (!p) return 1;
   e->launch_count = 0;
   const size_t bytes = static_cast<size_t>(B) * frame_h * frame_w * 3;
+  const int slot = (flags & UVLT_FRAME_SLOT1) ? 1 : 0;
   if (frames_host) {
-    if (grow_frame_stage(e, bytes, s)) return 1;
-    ENG_CUDA(cudaMemcpyAsync(e->frame_stage, frames_host, bytes, cudaMemcpyHostToDevice, s));
-  } else if (bytes > e->frame_stage_bytes) {  // frames_host == NULL: the frames were sent with uvlt_upload_frames
+    if (grow_frame_stage(e, bytes, s, slot)) return 1;
+    ENG_CUDA(cudaMemcpyAsync(e->frame_stage_[slot], frames_host, bytes, cudaMemcpyHostToDevice, s));
+  } else if (bytes > e->frame_stage_bytes_[slot]) {  // frames_host == NULL: the frames were sent with uvlt_upload_frames*
     set_error("uvlt_track_frame_image_host: no frames uploaded for this batch / frame size");
     return 1;
   }
-  CropParams cp{e->frame_stage, frame_h, frame_w, state, search_factor, e->Hx, e->u8_stage, e->rf_d};
+  CropParams cp{e->frame_stage_[slot], frame_h, frame_w, state, search_factor, e->Hx, e->u8_stage, e->rf_d};
   UVLT_LAUNCH(crop_resize_kernel, dim3((e->Hx * e->Hx + 255) / 256, B), dim3(256), 0, s, cp);
   if (cudaGetLastError() != cudaSuccess) { set_error("crop_resize launch failed"); return 1; }
   ++e->launch_count;
@@ -1204,7 +1208,20 @@ int uvlt_upload_frames(uvlt_handle e, const uint8_t* host, int64_t dst_offset, i
   if (dst_offset < 0 || nbytes < 0 || dst_offset + nbytes > total_bytes) { set_error("uvlt_upload_frames: bad range"); return 1; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s)) return 1;
-  ENG_CUDA(cudaMemcpyAsync(e->frame_stage + dst_offset, host, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, s));
+  ENG_CUDA(cudaMemcpyAsync(e->frame_stage_[0] + dst_offset, host, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int uvlt_upload_frames_slot(uvlt_handle e, const uint8_t* host, int64_t dst_offset, int64_t nbytes, int64_t total_bytes,
+                            int32_t slot, void* stream) {
+  if (!e || !host) { set_error("uvlt_upload_frames_slot: null argument"); return 1; }
+  if (slot < 0 || slot > 1 || dst_offset < 0 || nbytes < 0 || dst_offset + nbytes > total_bytes) {
+    set_error("uvlt_upload_frames_slot: bad range or slot");
+    return 1;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s, slot)) return 1;
+  ENG_CUDA(cudaMemcpyAsync(e->frame_stage_[slot] + dst_offset, host, static_cast<size_t>(nbytes), cudaMemcpyHostToDevice, s));
   return 0;
 }
 
@@ -1219,7 +1236,7 @@ int uvlt_upload_frames_2d(uvlt_handle e, const uint8_t* host, int64_t src_pitch,
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (grow_frame_stage(e, static_cast<size_t>(total_bytes), s)) return 1;
-  ENG_CUDA(cudaMemcpy2DAsync(e->frame_stage + dst_offset, static_cast<size_t>(dst_pitch), host,
+  ENG_CUDA(cudaMemcpy2DAsync(e->frame_stage_[0] + dst_offset, static_cast<size_t>(dst_pitch), host,
                              static_cast<size_t>(src_pitch), static_cast<size_t>(width_bytes), static_cast<size_t>(rows),
                              cudaMemcpyHostToDevice, s));
   return 0;

@@ -180,20 +180,31 @@ def run_dataset_batched(dataset: Seq[Sequence], tracker: Tracker, batch: int, ra
         outs = [{"target_bbox": [s.init_info()["init_bbox"]], "time": [time.time() - t0]} for s in group]
         dead = [None] * len(seqs)
         last = [None] * len(seqs)
+        next_cache = [None]
         n_max = max(len(s) for s in group)
         for t in range(1, n_max):
             t0 = time.time()
             frames = []
+            cached = next_cache[0][1] if next_cache[0] is not None and next_cache[0][0] == t else None
             for b, s in enumerate(seqs):
                 try:
                     if dead[b] is None:
-                        last[b] = read_image(s.frames[min(t, len(s) - 1)])
+                        # reuse the very array objects handed to the tracker as `next_images` (it recognises them)
+                        last[b] = cached[b] if cached is not None else read_image(s.frames[min(t, len(s) - 1)])
                 except Exception as e:  # an unreadable frame ends this sequence only
                     dead[b] = f"{type(e).__name__}: {e}"
                 if last[b] is None:
                     last[b] = read_image(s.frames[0])
                 frames.append(last[b])
-            res = bt.track(frames, raise_on_failure=False)
+            # the frames of step t+1 are known: let the tracker upload them while step t computes
+            nxt = None
+            if t + 1 < n_max and all(d is None for d in dead):
+                try:
+                    nxt = [read_image(s.frames[min(t + 1, len(s) - 1)]) for s in seqs]
+                    next_cache[0] = (t + 1, nxt)
+                except Exception:
+                    nxt = None
+            res = bt.track(frames, raise_on_failure=False, next_images=nxt)
             dt = (time.time() - t0) / len(group)
             for b, s in enumerate(group):
                 if dead[b] is None and res[b].get("failed"):
