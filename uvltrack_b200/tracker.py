@@ -431,8 +431,9 @@ class BatchTracker:
             if pf is not None:
                 fut, pf_images, pf_slot, pf_hw = pf
                 nbytes = fut.result()  # staging + enqueue finished (normally long ago: it ran under the last forward)
+                # whatever happens next to that staging slot happens after the prefetch copies have landed
+                torch.cuda.current_stream().wait_event(self._pf_events[pf_slot])
                 if pf_hw == (H, W) and len(pf_images) == len(images) and all(a is b for a, b in zip(pf_images, images)):
-                    torch.cuda.current_stream().wait_event(self._pf_events[pf_slot])
                     use_slot, prefetched = pf_slot, True
                     self.h2d_bytes += nbytes
 
