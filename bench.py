@@ -489,10 +489,16 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_s = t1 - t0
+    per_rank = None
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+        # after the timed region: where each rank spent its loop (rank skew shows up as waiting in the final gather)
+        mine = {"rank": rank, "track_loop_ms": round((t_track - t0) * 1e3, 3), "gather_wait_ms": round((t1 - t_track) * 1e3, 3),
+                **{k: round((tracker.phase_s[k] - ph0[k]) * 1e3, 3) for k in ("stage_h2d", "engine")}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     assert all_traj.shape[0] == B * world and bool(torch.isfinite(all_traj).all())
     phases = {k: round((tracker.phase_s[k] - ph0[k]) / steps * 1e3, 4) for k in tracker.phase_s}
     phases["python_loop_other"] = round(((t_track - t0) - sum(tracker.phase_s[k] - ph0[k] for k in ph0)) / steps * 1e3, 4)
@@ -509,6 +515,7 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
                 "frame_bytes_per_step": int(B * np.prod(seqs[0][0][0].shape)),
                 "d2h_bytes_per_step": B * 80, "ms_per_step": round(e2e_s / steps * 1e3, 4)},
         "e2e_phases_ms_per_step": phases,
+        "e2e_per_rank_totals_ms": per_rank,
         "launches_per_step": int(launches_per_step),
         "gpu_launches": int(launches_per_step * steps + e2e_launches),
         "skip_dead_text_branch": skip_text, "text_branch_cached_per_sequence": text_cached,
@@ -591,6 +598,7 @@ def run_b200(a):
                     "crop+resize bit-exact with cv2, forward_test, window merge, map_box_back / clip_box) -> D2H of the "
                     "[B,10] fp64 rows; prompt update every 20 frames; ONE final trajectory all-gather included"),
         "e2e_phases_ms_per_step": prim["e2e_phases_ms_per_step"],
+        "e2e_per_rank_totals_ms": prim["e2e_per_rank_totals_ms"],
         "gpu_launches": prim["gpu_launches"] + sum(w["gpu_launches"] for w in extra.values()),
         "launches_per_step": prim["launches_per_step"],
         "clocks": clk, "roofline": prim["roofline"], "roofline_attention": prim["roofline_attention"],
