@@ -192,6 +192,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  // SPLIT: CTA 1 stores its partial into CTA 0's shared memory at the end.  A cluster's CTAs are co-scheduled, but a
+  // distributed-shared-memory access is only defined once the target CTA has started executing: one cluster barrier up
+  // front makes that explicit (compute-sanitizer racecheck: "block that might not have entered yet").
+  if (SPLIT) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;             // 64 columns

@@ -357,26 +357,22 @@ class BatchTracker:
             "snapshot": self.snapshot.data_ptr(), "out10": self.out10.data_ptr(),
         }
 
-    def _prefetch_job(self, images, slot, H, W):
-        """Worker-thread half of the double buffering: next step's frames -> pinned staging[slot] -> device staging
-        slot on the copy stream, then an event the next track() makes its stream wait on.  Whole frames are sent (the
-        next search window depends on the box this step is still computing)."""
-        import torch
-
+    def _prefetch_job(self, images, slot, H, W, b0, b1):
+        """Worker-thread half of the double buffering: frames [b0, b1) of the next step -> pinned staging[slot] -> device
+        staging slot on the copy stream.  Whole frames are sent (the next search window depends on the box this step is
+        still computing).  Several of these run in parallel on the pool; the event the next track() waits on is recorded
+        by the caller once all of them have enqueued their copies."""
         lib, h = self.engine.lib, self.engine.h
-        buf = self._pf_frames[slot]
         per = H * W * 3
         total = self.B * per
         stream = self._pf_stream.cuda_stream
-        base = buf.data_ptr()
+        base = self._pf_frames[slot].data_ptr()
         arr = self._pf_np[slot]
-        for b in range(self.B):
+        for b in range(b0, b1):
             np.copyto(arr[b], images[b])
             if lib.uvlt_upload_frames_slot(h, base + b * per, b * per, per, total, slot, stream):
                 raise RuntimeError("uvlt_upload_frames_slot failed")
-        ev = self._pf_events[slot]
-        ev.record(self._pf_stream)
-        return total
+        return (b1 - b0) * per
 
     def track(self, images, raise_on_failure: bool = True, next_images=None):
         """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch.
@@ -429,9 +425,10 @@ class BatchTracker:
             use_slot = 0
             prefetched = False
             if pf is not None:
-                fut, pf_images, pf_slot, pf_hw = pf
-                nbytes = fut.result()  # staging + enqueue finished (normally long ago: it ran under the last forward)
+                futs, pf_images, pf_slot, pf_hw = pf
+                nbytes = sum(f_.result() for f_ in futs)  # staging + enqueue finished (normally long ago: under the last forward)
                 # whatever happens next to that staging slot happens after the prefetch copies have landed
+                self._pf_events[pf_slot].record(self._pf_stream)
                 torch.cuda.current_stream().wait_event(self._pf_events[pf_slot])
                 if pf_hw == (H, W) and len(pf_images) == len(images) and all(a is b for a, b in zip(pf_images, images)):
                     use_slot, prefetched = pf_slot, True
@@ -469,8 +466,11 @@ class BatchTracker:
                 if self._pf_stream is None:
                     self._pf_stream = torch.cuda.Stream()
                     self._pf_events = [torch.cuda.Event(), torch.cuda.Event()]
-                self._pf_pending = (self._pool.submit(self._prefetch_job, list(next_images), nslot, H, W), list(next_images),
-                                    nslot, (H, W))
+                nxt = list(next_images)
+                njobs = min(4, self.B)
+                cuts = [self.B * k // njobs for k in range(njobs + 1)]
+                self._pf_pending = ([self._pool.submit(self._prefetch_job, nxt, nslot, H, W, cuts[k], cuts[k + 1])
+                                     for k in range(njobs)], nxt, nslot, (H, W))
             t_staged = time.perf_counter()
             rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
                                                  f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
