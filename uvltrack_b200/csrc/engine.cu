@@ -101,6 +101,8 @@ struct uvlt_engine {
   // activations
   float* x = nullptr;
   float* xpart = nullptr;  // [splits - 1][B, N, D] split-K partial products of fc2 (same offsets as x)
+  bool head_conv = false;            // box-head convolutions as implicit GEMMs (no im2col); see GemmShape::conv_S
+  __nv_bfloat16* srch_bf = nullptr;  // [B, SS, D] bf16 copy of the search rows (A operand of the first conv)
   float* head_part = nullptr;  // [head0_splits][B*SS, 4C] raw partial products of the head's first conv GEMM
   int head0_splits = 1;        // > 1 only for small max_batch (the GEMM is 16 tiles of 108 k-blocks at B = 1)
   float* text_cache = nullptr;  // [B, T, D] text rows after the last BERT-only layer (constant per sequence)
@@ -174,8 +176,13 @@ int alloc_activations(uvlt_engine* e) {
   const size_t cout[4] = {C, C / 2, C / 4, C / 8};
   e->head0_splits = pick_head_splits(static_cast<int>(B * SS), static_cast<int>(4 * C), static_cast<int>(9 * D));
   if (e->head0_splits > 1 && dalloc(e, &e->head_part, e->head0_splits * B * SS * 4 * C)) return 1;
+  // UVLT_HEAD_CONV=0 keeps the im2col formulation (A/B timing, and the path for grids the window boxes do not fit)
+  const char* hc = std::getenv("UVLT_HEAD_CONV");
+  e->head_conv = !(hc && hc[0] == '0') && conv3x3_implicit_ok(e->S, static_cast<int>(D)) &&
+                 conv3x3_implicit_ok(e->S, static_cast<int>(C / 4));
+  if (e->head_conv && dalloc(e, &e->srch_bf, B * SS * D)) return 1;
   for (int l = 0; l < 4; ++l) {
-    if (dalloc(e, &e->col[l], (l == 0 ? 1 : 4) * B * SS * 9 * cin[l])) return 1;
+    if (!e->head_conv && dalloc(e, &e->col[l], (l == 0 ? 1 : 4) * B * SS * 9 * cin[l])) return 1;
     if (dalloc(e, &e->y[l], B * SS * 4 * cout[l])) return 1;
   }
   if (dalloc(e, &e->cls_map, B * SS) || dalloc(e, &e->bbox_map, B * SS * 4) || dalloc(e, &e->cont_score, B * SS * 3) ||
@@ -483,10 +490,13 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
       ep.out_ld = 4 * C;
       ep.split_out = e->head_part + static_cast<long long>(e->Bm) * e->SS * 4 * C;
       ep.split_stride = static_cast<long long>(e->Bm) * e->SS * 4 * C;
-      if (gemm_prepare(&p->head[0], e->col[0], 9 * D, 0, e->head_w[0], 9 * D, 0, M, 4 * C, 9 * D, 1, 64, ep, hs))
+      if (e->head_conv ? gemm_prepare_conv3x3(&p->head[0], e->srch_bf, D, e->S, B, D, e->head_w[0], 0, 4 * C, 1, 64, ep, hs)
+                       : gemm_prepare(&p->head[0], e->col[0], 9 * D, 0, e->head_w[0], 9 * D, 0, M, 4 * C, 9 * D, 1, 64, ep, hs))
         return nullptr;
-    } else if (prep(e, &p->head[0], e->col[0], e->head_w[0], M, 4 * C, 9 * D,
-                    ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU))) {
+    } else if (e->head_conv ? gemm_prepare_conv3x3(&p->head[0], e->srch_bf, D, e->S, B, D, e->head_w[0], 0, 4 * C, 1,
+                                                   e->force_bn, ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU))
+                            : prep(e, &p->head[0], e->col[0], e->head_w[0], M, 4 * C, 9 * D,
+                                   ep_bf16(e->head_b[0], e->y[0], 4 * C, ACT_RELU))) {
       return nullptr;
     }
     for (int l = 1; l < 4; ++l) {
@@ -494,8 +504,10 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
       ep.bias_gstride = cout[l];
       ep.out_gstride = cout[l];
       const int K = 9 * cin[l];
-      if (prep(e, &p->head[l], e->col[l], e->head_w[l], M, cout[l], K, ep, 4, static_cast<long long>(M) * K,
-               static_cast<long long>(cout[l]) * K))
+      if (e->head_conv ? gemm_prepare_conv3x3(&p->head[l], e->y[l - 1], 4 * cin[l], e->S, B, cin[l], e->head_w[l],
+                                              static_cast<long long>(cout[l]) * K, cout[l], 4, e->force_bn, ep)
+                       : prep(e, &p->head[l], e->col[l], e->head_w[l], M, cout[l], K, ep, 4, static_cast<long long>(M) * K,
+                              static_cast<long long>(cout[l]) * K))
         return nullptr;
     }
   }
@@ -663,6 +675,32 @@ int run_head(uvlt_engine* e, Plan* p, cudaStream_t s, bool train_branch) {
   const int cin[4] = {D, C, C / 2, C / 4};
   const int cout[4] = {C, C / 2, C / 4, C / 8};
   for (int l = 0; l < 4; ++l) {
+    if (e->head_conv) {
+      // implicit-GEMM convolutions: the GEMM's TMA producer reads the shifted windows of the feature map itself; only
+      // the first layer needs its input (fp32 search rows of the token stream) as a bf16 tensor
+      if (l == 0) {
+        const long long n8 = static_cast<long long>(B) * e->SS * D / 8;
+        UVLT_LAUNCH(search_to_bf16_kernel, dim3(static_cast<unsigned>((n8 + 255) / 256)), dim3(256), 0, s, e->x,
+                    static_cast<long long>(e->N) * D, 1 + e->Nz, e->SS, D, B, e->srch_bf);
+        if (cudaGetLastError() != cudaSuccess) { set_error("search_to_bf16 launch failed"); return 1; }
+        ++e->launch_count;
+      }
+      RUN(gemm_launch(p->head[l], s));
+      if (l == 0 && p->head[0].shape.splits > 1) {
+        SplitReduceParams rp{};
+        rp.part = e->head_part;
+        rp.stride = static_cast<long long>(e->Bm) * e->SS * 4 * C;
+        rp.splits = p->head[0].shape.splits;
+        rp.bias = e->head_b[0];
+        rp.out = e->y[0];
+        rp.total = static_cast<long long>(B) * e->SS * 4 * C;
+        rp.N = 4 * C;
+        rp.relu = 1;
+        if (launch_splitk_reduce(rp, s)) { set_error("splitk_reduce launch failed"); return 1; }
+        ++e->launch_count;
+      }
+      continue;
+    }
     Im2col3Params ip{};
     if (l == 0) {
       ip.src = e->x; ip.src_f32 = 1;

@@ -49,6 +49,14 @@ struct GemmShape {
   int stages;  // depth of the smem operand ring (2..GEMM_MAX_STAGES), chosen on the host from the grid size
   int splits;  // K is cut into `splits` equal ranges, one CTA each (blockIdx.z = group * splits + split)
   int groups;  // read by the persistent CTA-pair kernel only (the one-tile kernels take the group from blockIdx.z)
+  // Implicit-GEMM 3x3 / pad 1 convolution over an S x S token grid (conv_S > 0): A is NOT an [M, K] matrix but the bf16
+  // feature map [B, S, S, groups * Cin] behind a 4-D tensor map with box {64 channels, S, 128 / S rows, 1}.  k-block kb
+  // covers tap = kb / conv_cb (ky = tap / 3, kx = tap % 3) and channels [(kb % conv_cb) * 64, +64) of group g; the 128
+  // output rows of an M tile are 128 / S whole image rows of one sequence, and the tap shifts the box by (kx - 1, ky - 1):
+  // out-of-range coordinates are the zero padding (TMA zero fill).  W keeps the (ky, kx, c) column order of the im2col
+  // formulation, so K = 9 * Cin and everything but the A load is unchanged.  Requires 128 % S == 0 and S * S % 128 == 0.
+  int conv_S;
+  int conv_cb;  // Cin / 64
 };
 
 constexpr int GEMM_MAX_STAGES = 12;
@@ -313,6 +321,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   pdl_trigger();
   if (threadIdx.x == 0) TRACE_PT(0x102);
 
+  // A tile of k-block `kbg` (global k-block index): a [128 x 64] box of the [M, K] matrix, or in convolution mode the
+  // window of the feature map shifted by the tap of this k-block (see GemmShape::conv_S)
+  auto load_a = [&](uint8_t* dst, uint64_t* bar, int kbg) {
+    if (shape.conv_S > 0) {
+      const int tap = kbg / shape.conv_cb;
+      const int c0 = (g * shape.conv_cb + (kbg - tap * shape.conv_cb)) * GEMM_BK;
+      const int SS = shape.conv_S * shape.conv_S;
+      const int b = m0 / SS;
+      const int y0 = (m0 - b * SS) / shape.conv_S;
+      tma_load_4d(dst, &tma_a, bar, c0, tap % 3 - 1, y0 + tap / 3 - 1, b);
+    } else {
+      tma_load_3d(dst, &tma_a, bar, kbg * GEMM_BK, m0, g);
+    }
+  };
   // The producer and MMA warps stay CONVERGED (uniform loop counters, all lanes wait on the barriers) and only the
   // asynchronous instruction is issued by one elected lane: under `if (lane == 0)` ptxas wraps every tcgen05.mma / TMA
   // instruction in an ELECT + R2UR.BROADCAST waterfall loop (see elect_one_sync in common.cuh).
@@ -326,7 +348,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             tma_load_3d_mc(smem + kb * S::STAGE_BYTES + crank * A_HALF, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK,
                            m0 + crank * (GEMM_BM / 2), g, 0x3);
           else
-            tma_load_3d(smem + kb * S::STAGE_BYTES, &tma_a, &full_bar[kb], (kb0 + kb) * GEMM_BK, m0, g);
+            load_a(smem + kb * S::STAGE_BYTES, &full_bar[kb], kb0 + kb);
         }
       }
       __syncwarp();
@@ -342,7 +364,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             tma_load_3d_mc(a_dst + crank * A_HALF, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0 + crank * (GEMM_BM / 2), g,
                            0x3);
           else
-            tma_load_3d(a_dst, &tma_a, &full_bar[s], (kb0 + kb) * GEMM_BK, m0, g);
+            load_a(a_dst, &full_bar[s], kb0 + kb);
           tma_load_3d(a_dst + S::A_BYTES, &tma_w, &full_bar[s], (kb0 + kb) * GEMM_BK, n0, g);
         }
         __syncwarp();
@@ -512,7 +534,15 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           if (elect_one_sync()) {
             uint8_t* a_dst = smem + s * STAGE_BYTES;
             if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-            tma_load_3d_2sm(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
+            if (shape.conv_S > 0) {  // implicit-GEMM convolution: shifted window of the feature map (GemmShape::conv_S)
+              const int tap = kb / shape.conv_cb;
+              const int SS = shape.conv_S * shape.conv_S;
+              const int b = m0 / SS;
+              tma_load_4d_2sm(a_dst, &tma_a, &full_bar[s], (g * shape.conv_cb + (kb - tap * shape.conv_cb)) * GEMM_BK,
+                              tap % 3 - 1, (m0 - b * SS) / shape.conv_S + tap / 3 - 1, b);
+            } else {
+              tma_load_3d_2sm(a_dst, &tma_a, &full_bar[s], kb * GEMM_BK, m0, g);
+            }
             tma_load_3d_2sm(a_dst + A_BYTES, &tma_w, &full_bar[s], kb * GEMM_BK, n0 + static_cast<int>(crank) * (BN / 2), g);
           }
           __syncwarp();

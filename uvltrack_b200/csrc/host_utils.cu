@@ -54,6 +54,31 @@ int make_tma_bf16_3d(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t
   return 0;
 }
 
+int make_tma_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4]) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
+    return 1;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides_bytes[0] & 15) || (strides_bytes[1] & 15) || (strides_bytes[2] & 15)) {
+    set_error("TMA operand base/strides must be 16-byte aligned");
+    return 1;
+  }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, st, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 1;
+  }
+  return 0;
+}
+
 static int g_num_sms = 148;
 // UVLT_ATTN_SPLIT=0 disables the key-split cluster variant of the attention kernel (A/B timing)
 static int g_attn_split = [] {
@@ -271,6 +296,32 @@ int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstri
     return 1;
   // the CTA-pair kernel stages one 128-row half of the 256-wide W tile per CTA
   if (make_tma_bf16_3d(&g->tma_w, W, K, N, groups, w_ld * 2, w_gstride * 2, g->two_sm ? GEMM2_BN / 2 : bn)) return 1;
+  return 0;
+}
+
+bool conv3x3_implicit_ok(int S, int Cin) {
+  return S > 0 && 128 % S == 0 && (S * S) % 128 == 0 && Cin % GEMM_BK == 0;
+}
+
+int gemm_prepare_conv3x3(GemmLaunch* g, const void* src, long long src_ld, int S, int B, int Cin, const void* W,
+                         long long w_gstride, int N, int groups, int bn, const GemmEpilogue& ep, int splits) {
+  if (!conv3x3_implicit_ok(S, Cin)) {
+    set_error("conv3x3: implicit GEMM needs 128 % S == 0, S * S % 128 == 0 and Cin % 64 == 0");
+    return 1;
+  }
+  const int M = B * S * S, K = 9 * Cin;
+  // the plain path builds every map and picks the kernel; its A map (over a fictitious [M, K] matrix at `src`) is then
+  // replaced by the 4-D window map.  a_ld = K keeps the 3-D encoder's stride checks satisfied.
+  if (gemm_prepare(g, src, K, static_cast<long long>(M) * K, W, K, w_gstride, M, N, K, groups, bn, ep, splits)) return 1;
+  if (g->multicast) g->multicast = false;  // the multicast variant loads half boxes of A: not defined for window boxes
+  const uint64_t dims[4] = {static_cast<uint64_t>(src_ld), static_cast<uint64_t>(S), static_cast<uint64_t>(S),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(src_ld) * 2, static_cast<uint64_t>(S) * src_ld * 2,
+                               static_cast<uint64_t>(S) * S * src_ld * 2};
+  const uint32_t box[4] = {64, static_cast<uint32_t>(S), static_cast<uint32_t>(128 / S), 1};
+  if (make_tma_bf16_4d(&g->tma_a, src, dims, strides, box)) return 1;
+  g->shape.conv_S = S;
+  g->shape.conv_cb = Cin / GEMM_BK;
   return 0;
 }
 

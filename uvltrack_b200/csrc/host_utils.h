@@ -47,6 +47,15 @@ struct GemmLaunch {
 // splits: 1 = no split-K; > 1 requires an fp32 output with ep.split_out set and K % (64 * splits) == 0.
 int gemm_prepare(GemmLaunch* g, const void* A, long long a_ld, long long a_gstride, const void* W, long long w_ld,
                  long long w_gstride, int M, int N, int K, int groups, int bn, const GemmEpilogue& ep, int splits = 1);
+// Implicit-GEMM 3x3 / pad 1 convolution over an S x S token grid (GemmShape::conv_S): src = bf16 feature map
+// [B, S*S, src_ld] whose channels [g * Cin, (g + 1) * Cin) feed group g; W [groups][N, 9 * Cin] in (ky, kx, c) column
+// order.  Same epilogues / split-K as gemm_prepare.  conv3x3_implicit_ok(S, Cin): the shapes this path supports (other
+// sizes go through im2col3x3_kernel + a plain GEMM).
+bool conv3x3_implicit_ok(int S, int Cin);
+int gemm_prepare_conv3x3(GemmLaunch* g, const void* src, long long src_ld, int S, int B, int Cin, const void* W,
+                         long long w_gstride, int N, int groups, int bn, const GemmEpilogue& ep, int splits = 1);
+int make_tma_bf16_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4]);
 // split-K factor for an [M, N, K] fp32-output GEMM whose consumer can add partials: > 1 only when the unsplit grid
 // would leave most SMs idle (small M) and K is long
 int pick_splits(int M, int N, int K);

@@ -310,6 +310,26 @@ static __global__ void __launch_bounds__(256) im2col3x3_kernel(const Im2col3Para
   }
 }
 
+// Search rows of the fp32 token stream -> bf16 [B, S*S, D]: the A operand of the box head's first implicit-GEMM
+// convolution (replaces the 9x larger im2col matrix)
+static __global__ void __launch_bounds__(256) search_to_bf16_kernel(const float* x, long long x_bstride, int row_off,
+                                                                    int rows, int D, int B, __nv_bfloat16* dst) {
+  pdl_wait();
+  pdl_trigger();
+  const long long per_seq8 = static_cast<long long>(rows) * D / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= per_seq8 * B) return;
+  const int b = static_cast<int>(i / per_seq8);
+  const long long o = (i - b * per_seq8) * 8;
+  const float* s = x + b * x_bstride + static_cast<long long>(row_off) * D + o;
+  const float4 a = *reinterpret_cast<const float4*>(s);
+  const float4 d = *reinterpret_cast<const float4*>(s + 4);
+  uint4 u;
+  u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+  u.z = pack_bf16x2(d.x, d.y); u.w = pack_bf16x2(d.z, d.w);
+  *reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * rows * D + o)) = u;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Key-ignore masks -> additive attention biases (modality_unified_feature_extractor.py:43-50, bert_backbone.py:746-748)
 //   visual [B, Nv]: cls, template ignored iff flag == 1          (masked_fill -1e10 dialect)
