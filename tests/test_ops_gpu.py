@@ -171,8 +171,27 @@ def test_attention_second_generation_kernel_matches(poly):
 
     env = dict(os.environ, UVLT_ATTN_V="2", UVLT_ATTN_POLY=poly)
     here = os.path.abspath(__file__)
-    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k", "test_attention and not second",
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k", "test_attention and not second and not third",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("grid", ["0", "5"])
+def test_attention_third_generation_kernel_matches(grid):
+    """attention3.cuh (persistent CTAs over (batch, head, tile pair) work items, two threads per query row; selected with
+    UVLT_ATTN_V=3) must pass the same parity cases as the default kernel.  UVLT_ATTN_SPLIT=0 sends every shape to it (by
+    default small grids keep the key-split variant of the first kernel); UVLT_ATTN_GRID=5 caps the grid so that every CTA
+    walks a long list of items: PAIR -> PAIR, PAIR -> LONE and LONE -> LONE hand-overs, Q / staging buffer reuse, barrier
+    phases running across items."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, UVLT_ATTN_V="3", UVLT_ATTN_SPLIT="0", UVLT_ATTN_GRID=grid)
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-m", "gpu", "-k",
+                        "test_attention and not second and not third", "-p", "no:cacheprovider"], env=env,
+                       capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 

@@ -95,7 +95,12 @@ static int g_attn_split = [] {
 // UVLT_ATTN_POLY=1: a quarter of v2's exponentials on the FMA pipe (no gain while the kernel is not MUFU bound).
 static int g_attn_v = [] {
   const char* e = getenv("UVLT_ATTN_V");
-  return (e && e[0] == '2') ? 2 : 1;
+  return (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : 1;
+}();
+// UVLT_ATTN_GRID=<n> caps the persistent grid of the third-generation kernel (tests: many work items per CTA)
+static int g_attn_grid_cap = [] {
+  const char* e = getenv("UVLT_ATTN_GRID");
+  return e ? atoi(e) : 0;
 }();
 static int g_attn_poly = [] {
   const char* e = getenv("UVLT_ATTN_POLY");
@@ -135,6 +140,8 @@ int init_kernel_attributes() {
                                     cudaSharedmemCarveoutMaxShared));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
   {
     int dev = 0, sms = 0;
     UVLT_CUDA_OK(cudaGetDevice(&dev));
@@ -422,10 +429,31 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   // small grids (decided from the engine's capacity, so that a sequence's result does not depend on the batch it shares
   // a call with): one query tile per CTA, the two slots split its key blocks
   a->p2.split_all = (g_attn_split && cb * H * ((n + AT2_BQ - 1) / AT2_BQ) <= g_num_sms) ? 1 : 0;
+  // third generation: persistent CTAs over (batch, head, tile pair) items; only where the grid fills the GPU (decided from
+  // the engine's capacity like the key split, so that a sequence's result does not depend on its batch)
+  {
+    const int ntiles = (n + AT3_BQ - 1) / AT3_BQ;
+    const int items = B * H * ((ntiles >> 1) + (ntiles & 1));
+    a->v3 = g_attn_v == 3 && !a->split;
+    a->grid3 = items < g_num_sms ? items : g_num_sms;
+    if (g_attn_grid_cap > 0 && a->grid3 > g_attn_grid_cap) a->grid3 = g_attn_grid_cap;
+    a->p3.n = n;
+    a->p3.H = H;
+    a->p3.B = B;
+    a->p3.scale_log2 = a->p.scale_log2;
+    a->p3.bias = bias;
+    a->p3.zero = 0;
+  }
   return 0;
 }
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
+  if (a.v3) {
+    if (a.poly) UVLT_LAUNCH(attention3_kernel<true>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3);
+    else UVLT_LAUNCH(attention3_kernel<false>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3);
+    UVLT_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (a.v2) {
     const int ntiles = (a.p2.n + AT2_BQ - 1) / AT2_BQ;
     dim3 grid2(a.p2.split_all ? ntiles : (ntiles + 1) / 2, a.p2.H, a.B);

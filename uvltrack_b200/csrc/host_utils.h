@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "gemm.cuh"
 
 namespace uvlt {
@@ -78,6 +79,11 @@ struct AttnLaunch {
   bool poly;   // a quarter of the exponentials on the FMA pipe
   Attn2Params p2;
   CUtensorMap tma_o;  // output [B, n, H*64] bf16, 128-row boxes (TMA bulk store of a query tile)
+  // third-generation kernel (attention3.cuh): persistent, two threads per query row; large grids only (small grids keep
+  // the key-split cluster variant of the first kernel)
+  bool v3;
+  int grid3;   // CTAs: min(SMs, work items)
+  Attn3Params p3;
 };
 // capacity_batch: the batch size the split decision is made for (the engine passes its max_batch, so that a sequence's
 // result does not depend on how many sequences share the call; 0 = use B)
