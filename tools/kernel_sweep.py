@@ -63,6 +63,9 @@ def gemm(Bs, n=513, D=768):
 
 
 def attn(Bs, ns=(513, 553, 321, 361), H=12):
+    if os.environ.get("SWEEP_NS"):  # e.g. SWEEP_NS=1193 SWEEP_H=16 for UVLTrack-L 384
+        ns = [int(v) for v in os.environ["SWEEP_NS"].split(",")]
+    H = int(os.environ.get("SWEEP_H", H))
     for B in Bs:
         for n in ns:
             qkv = torch.randn(B, n, 3 * H * 64, device="cuda").to(torch.bfloat16)

@@ -150,7 +150,68 @@ __device__ __forceinline__ void at3_chunk_ex2_m(uint32_t (&v)[32], float scale, 
   }
 }
 
-template <bool POLY>
+// ---- packed fp32 pairs (FFMA2 / FADD2, sm_100): half the FMA-pipe issue slots of the scale-and-subtract and of the row
+//      sums; the 64 scores of a thread arrive from tcgen05.ld in consecutive registers, so (2i, 2i+1) are aligned pairs ----
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for a pair on the FMA pipe (same Cody-Waite split and degree-3 polynomial as ex2_poly3 in attention2.cuh)
+__device__ __forceinline__ void ex2_poly3_x2(float& y0, float& y1, float x0, float x1) {
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, 12582912.0f, 12582912.0f);
+  fadd2(n0, n1, t0, t1, -12582912.0f, -12582912.0f);
+  ffma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);
+  ffma2(p0, p1, f0, f1, 0.05508868f, 0.05508868f, 0.24260405f, 0.24260405f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.69327623f, 0.69327623f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.99992895f, 0.99992895f);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// exponentials of a full unbiased 32-column chunk, in place; NPOLY of its 16 pairs take the FMA-pipe polynomial
+template <int NPOLY>
+__device__ __forceinline__ void at3_chunk_ex2_x2(uint32_t (&v)[32], float scale, float neg_ref) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float x0, x1, y0, y1;
+    ffma2(x0, x1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), scale, scale, neg_ref, neg_ref);
+    // spread the polynomial pairs evenly over the chunk
+    const bool poly = NPOLY > 0 && (((i >> 1) * NPOLY) % 16) + NPOLY > 15;
+    if (poly) {
+      ex2_poly3_x2(y0, y1, x0, x1);
+    } else {
+      y0 = ex2_approx(x0);
+      y1 = ex2_approx(x1);
+    }
+    v[i] = __float_as_uint(y0);
+    v[i + 1] = __float_as_uint(y1);
+  }
+}
+__device__ __forceinline__ float at3_chunk_sum_pack_x2(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    fadd2(a0, a1, a0, a1, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    fadd2(b0, b1, b0, b1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    pk[i >> 1] = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    pk[(i >> 1) + 1] = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+  }
+  return (a0 + a1) + (b0 + b1);
+}
+
+// VAR (UVLT_ATTN_POLY): 0 scalar FFMA / FADD, all exponentials on the MUFU; 1 the same with every fourth exponential on
+// the FMA pipe; 2 packed FFMA2 / FADD2; 3 / 4 / 5 packed + 4 / 6 / 8 of every 16 pairs on the FMA pipe
+template <int VAR>
 static __global__ void __launch_bounds__(AT3_THREADS, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out,
                   const Attn3Params p) {
@@ -366,6 +427,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
     const int pair_bar = 1 + t * 4 + quad;  // the two warps (halves) of one (slot, quadrant)
     const int slot_bar = 9 + t;             // the slot's 8 softmax warps
     constexpr int XO_FULL = 11, XO_FREE = 12;
+    constexpr int NPOLY = VAR == 3 ? 4 : VAR == 4 ? 6 : VAR == 5 ? 8 : 0;
     float* const mx = reinterpret_cast<float*>(smem + Attn3Smem::OFF_MX);
     float* const ls = reinterpret_cast<float*>(smem + Attn3Smem::OFF_LS);
     float* const ms = reinterpret_cast<float*>(smem + Attn3Smem::OFF_MS);
@@ -426,12 +488,14 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         //      the stages, i.e. separate scheduling regions (see at2_chunk_ex2) ----
         if (nchunk > 0) {
           if (gen0) at3_chunk_ex2_m(v[0], scale, neg_ref, bv0, lim0);
-          else at2_chunk_ex2<0, POLY>(v[0], scale, neg_ref, 0, 32);
+          else if (VAR >= 2) at3_chunk_ex2_x2<NPOLY>(v[0], scale, neg_ref);
+          else at2_chunk_ex2<0, VAR == 1>(v[0], scale, neg_ref, 0, 32);
         }
         if (p.zero) break;
         if (nchunk > 1) {
           if (gen1) at3_chunk_ex2_m(v[1], scale, neg_ref, bv1, lim0 - 32);
-          else at2_chunk_ex2<0, POLY>(v[1], scale, neg_ref, 0, 32);
+          else if (VAR >= 2) at3_chunk_ex2_x2<NPOLY>(v[1], scale, neg_ref);
+          else at2_chunk_ex2<0, VAR == 1>(v[1], scale, neg_ref, 0, 32);
         }
         if (i > 0) {
           // P_t and O_t are free once PV_t of the previous block has drained (the exponentials were computed meanwhile)
@@ -452,12 +516,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         }
         float l_blk = 0.0f;
         if (nchunk > 0) {
-          l_blk += at2_chunk_sum_pack(v[0], pk);
+          l_blk += VAR >= 2 ? at3_chunk_sum_pack_x2(v[0], pk) : at2_chunk_sum_pack(v[0], pk);
           tmem_st16(tP, pk);
         }
         if (p.zero) break;
         if (nchunk > 1) {
-          l_blk += at2_chunk_sum_pack(v[1], pk);
+          l_blk += VAR >= 2 ? at3_chunk_sum_pack_x2(v[1], pk) : at2_chunk_sum_pack(v[1], pk);
           tmem_st16(tP + 16, pk);
         }
         l_run = l_run * alpha + l_blk;

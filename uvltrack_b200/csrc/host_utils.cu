@@ -104,7 +104,7 @@ static int g_attn_grid_cap = [] {
 }();
 static int g_attn_poly = [] {
   const char* e = getenv("UVLT_ATTN_POLY");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh)
 }();
 
 // cudaFuncSetAttribute applies to the CURRENT device: the opt-in is tracked per device ordinal, so a process that creates
@@ -140,8 +140,9 @@ int init_kernel_attributes() {
                                     cudaSharedmemCarveoutMaxShared));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL));
+#define UVLT_AT3_ATTR(VAR) \
+  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL))
+  UVLT_AT3_ATTR(0); UVLT_AT3_ATTR(1); UVLT_AT3_ATTR(2); UVLT_AT3_ATTR(3); UVLT_AT3_ATTR(4); UVLT_AT3_ATTR(5);
   {
     int dev = 0, sms = 0;
     UVLT_CUDA_OK(cudaGetDevice(&dev));
@@ -157,7 +158,7 @@ int init_kernel_attributes() {
 // L2 bandwidth and only adds the cross-CTA slot handshake.  UVLT_MULTICAST=1 enables it for experiments.
 int g_gemm_multicast = [] {
   const char* e = getenv("UVLT_MULTICAST");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh)
 }();
 
 // CTA-pair persistent GEMM (gemm_bf16_tn_2sm_kernel): UVLT_GEMM_2SM=0 never, 1 by the rule below (default), 2 wherever
@@ -416,7 +417,8 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   const int cb = capacity_batch > 0 ? capacity_batch : B;
   a->split = g_attn_split && cb * H * ((n + ATT_BQ - 1) / ATT_BQ) <= g_num_sms && (n + ATT_BKV - 1) / ATT_BKV >= 2;
   a->v2 = g_attn_v == 2;
-  a->poly = g_attn_poly != 0;
+  a->poly = g_attn_poly == 1;
+  a->var3 = g_attn_poly <= 5 ? g_attn_poly : 0;
   a->p2.n = n;
   a->p2.H = H;
   a->p2.scale_log2 = a->p.scale_log2;
@@ -449,8 +451,16 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
 
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
   if (a.v3) {
-    if (a.poly) UVLT_LAUNCH(attention3_kernel<true>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3);
-    else UVLT_LAUNCH(attention3_kernel<false>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3);
+#define UVLT_AT3_LAUNCH(VAR) \
+  UVLT_LAUNCH(attention3_kernel<VAR>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3)
+    switch (a.var3) {
+      case 1: UVLT_AT3_LAUNCH(1); break;
+      case 2: UVLT_AT3_LAUNCH(2); break;
+      case 3: UVLT_AT3_LAUNCH(3); break;
+      case 4: UVLT_AT3_LAUNCH(4); break;
+      case 5: UVLT_AT3_LAUNCH(5); break;
+      default: UVLT_AT3_LAUNCH(0); break;
+    }
     UVLT_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -83,6 +83,7 @@ struct AttnLaunch {
   // the key-split cluster variant of the first kernel)
   bool v3;
   int grid3;   // CTAs: min(SMs, work items)
+  int var3;    // softmax arithmetic variant (UVLT_ATTN_POLY, attention3.cuh)
   Attn3Params p3;
 };
 // capacity_batch: the batch size the split decision is made for (the engine passes its max_batch, so that a sequence's
