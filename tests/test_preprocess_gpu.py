@@ -130,16 +130,21 @@ def test_prefetched_frames_give_identical_tracks():
     seqs = [synthetic_sequence(n + 1, seed=70 + b) for b in range(B)]
     infos = [{"init_bbox": s[1][0]} for s in seqs]
     tracks = {}
-    for mode in ("plain", "prefetch", "broken_promise"):
+    from uvltrack_b200.tracker import PinnedFrame, pinned_frames
+
+    pinned = [pinned_frames(s[0]) for s in seqs]  # the same clips in page-locked memory: uploaded without staging
+    assert all(isinstance(f, PinnedFrame) and np.array_equal(f, g) for fs, s in zip(pinned, seqs) for f, g in zip(fs, s[0]))
+    for mode in ("plain", "prefetch", "broken_promise", "pinned_plain", "pinned_prefetch"):
         bt = BatchTracker(params, batch=B)
         bt.initialize([s[0][0] for s in seqs], infos)
         out = []
+        src = pinned if mode.startswith("pinned") else [s[0] for s in seqs]
         for t in range(1, n + 1):
-            cur = [s[0][t] for s in seqs]
-            nxt = [s[0][t + 1] for s in seqs] if t < n else None
-            if mode == "plain":
+            cur = [f[t] for f in src]
+            nxt = [f[t + 1] for f in src] if t < n else None
+            if mode in ("plain", "pinned_plain"):
                 res = bt.track(cur)
-            elif mode == "prefetch":
+            elif mode in ("prefetch", "pinned_prefetch"):
                 res = bt.track(cur, next_images=nxt)
             else:  # announce frame t+1 of the OTHER sequence order: the tracker must notice and stage `cur` itself
                 res = bt.track(cur, next_images=nxt[::-1] if nxt else None)
@@ -148,3 +153,5 @@ def test_prefetched_frames_give_identical_tracks():
         bt.engine.close()
     assert np.array_equal(tracks["plain"], tracks["prefetch"])
     assert np.array_equal(tracks["plain"], tracks["broken_promise"])
+    assert np.array_equal(tracks["plain"], tracks["pinned_plain"])
+    assert np.array_equal(tracks["plain"], tracks["pinned_prefetch"])

@@ -35,7 +35,8 @@ def name(tag):
     who = {3: "MMA A", 4: "MMA B", 5: "SM  A", 6: "SM  B"}[tag >> 8]
     ph, i = (tag >> 4) & 0xf, tag & 0xf
     if tag >> 8 in (3, 4): what = {1: "QK issued", 2: "p_full seen", 3: "PV issued"}[ph]
-    else: what = {1: "s_full seen", 2: "reference known", 3: "pv_done seen", 4: "P stored", 6: "item stored"}[ph]
+    elif ph == 6: return who + " epilogue: " + {0: "item stored", 1: "last PV done", 2: "row sums exchanged", 3: "staging rows written", 4: "fenced", 5: "slot barrier passed"}.get(i, str(i))
+    else: what = {1: "s_full seen", 2: "reference known", 3: "pv_done seen", 4: "P stored", 7: "turn acquired", 8: "exponentials done"}[ph]
     return f"{who} {what} [{i}]"
 for tag, c in sorted(rows, key=lambda x: x[1]):
     print(f"{c - t0:8d}  {name(tag)}")

@@ -13,6 +13,6 @@ echo "launch list rc=$?"
 timeout 600 $NCU --set full --import-source on -k regex:gemm_bf16 -s 300 -c 4 -f -o gpurun_out/${TAG}_gemm \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_gemm.log 2>&1
 echo "gemm capture rc=$?"
-timeout 600 $NCU --set full --import-source on -k regex:attention_kernel -s 60 -c 2 -f -o gpurun_out/${TAG}_attn \
+timeout 600 $NCU --set full --import-source on -k regex:attention -s 60 -c 2 -f -o gpurun_out/${TAG}_attn \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_attn.log 2>&1
 echo "attn capture rc=$?"

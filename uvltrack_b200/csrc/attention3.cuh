@@ -59,6 +59,7 @@ struct Attn3Params {
   float scale_log2;
   const float* bias;
   int zero;  // always 0: an opaque branch condition that separates scheduling regions (see at2_chunk_ex2)
+  int pingpong;  // 1: the two slots take turns on the MUFU (named-barrier token around the exponentials of a block)
 };
 
 struct At3Item {
@@ -228,7 +229,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
   uint64_t* const s_free = s_full + 2;                // [2] the slot's 8 softmax warps hold S_t in registers
   uint64_t* const p_full = s_free + 2;                // [2] P_t stored (and O_t rescaled), 8 warp arrivals
   uint64_t* const pv_done = p_full + 2;               // [2] PV_t drained: P_t reusable, O_t includes the block
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* const stagger = pv_done + 2;              // slot 0 is half way through its very first block (8 warp arrivals)
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -250,6 +252,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
       mbar_init(&p_full[t], 8);
       mbar_init(&pv_done[t], 1);
     }
+    mbar_init(stagger, 8);
     for (int s = 0; s < AT3_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 2);
@@ -271,9 +274,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
   // and the four softmax warpgroups (64 scores per thread live in registers) take it.
 #if AT3_SETMAXNREG
   if (warp >= AT3_SM_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   }
 #endif
   if (warp == AT3_SM_WARPS) {
@@ -380,6 +383,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
       }
     };
     c_seek();
+    // slot 1 starts half a block behind slot 0 (only when its first item is a PAIR item: in a LONE item it has the
+    // shorter half of the key blocks anyway)
+    if (t == 1 && c_idx < geo.total && !c_it.lone) mbar_wait_trap(stagger, 0);
     issue_next_qk();
     int ord = 0;
 #pragma unroll 1
@@ -396,13 +402,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         const uint64_t vd = vd_base + STAGE_STEP * (c % AT3_STAGES);
         const int ksteps = (it.jb(t) + i == nblk - 1) ? ((last_valid + 15) >> 4) : (AT3_BK / 16);
         if (elect_one_sync()) {
-          if (ksteps == AT3_BK / 16) {
 #pragma unroll
-            for (int k = 0; k < AT3_BK / 16; ++k) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
-          } else {
-#pragma unroll 1
-            for (int k = 0; k < ksteps; ++k) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < AT3_BK / 16; ++k)
+            if (k < ksteps) umma_bf16_ts(tO, tP + 8 * k, vd + 128 * k, idesc_pv, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&kv_empty[c % AT3_STAGES]);
           if (it.lone) umma_commit(&kv_empty[c % AT3_STAGES]);  // LONE: the stage belongs to this slot alone
           umma_commit(&pv_done[t]);
@@ -415,57 +417,63 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
     if (lane == 0) TRACE_FLUSH();
   } else if (warp < AT3_SM_WARPS) {
     // ---------------- softmax / correction / epilogue warps ----------------
-    const int t = warp >> 3;           // slot
-    const int hf = (warp >> 2) & 1;    // which 64 of the block's 128 key columns
-    const int quad = warp & 3;         // TMEM lane quadrant
-    const int row = quad * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + t * 256 + lane_off + hf * 64;
-    const uint32_t tP = tmem_base + t * 256 + lane_off + 128 + hf * 32;
-    const uint32_t tO = tmem_base + t * 256 + lane_off + 192 + hf * 32;
-    const float scale = p.scale_log2;
-    const int pair_bar = 1 + t * 4 + quad;  // the two warps (halves) of one (slot, quadrant)
-    const int slot_bar = 9 + t;             // the slot's 8 softmax warps
-    constexpr int XO_FULL = 11, XO_FREE = 12;
+    // Register discipline: 64 scores per thread are live through a block, the cap is 96 registers (640 threads), and a
+    // spill is expensive here (213 KB of shared memory leave ~28 KB of L1, so local memory lives in L2: the first
+    // version spent ~8k cycles per work item reloading spilled loop-invariant values in its epilogue).  So nothing that
+    // can be re-derived is kept across the block loop: thread coordinates come from a volatile %tid.x read at each
+    // point of use (ptxas cannot hoist it), shared memory is addressed through 32-bit shared-space offsets, the work
+    // item is decoded again in the epilogue.
+    constexpr int XO_FULL = 11, XO_FREE = 12, EXP_TURN = 13;  // EXP_TURN + slot: that slot may run its exponentials
     constexpr int NPOLY = VAR == 3 ? 4 : VAR == 4 ? 6 : VAR == 5 ? 8 : 0;
-    float* const mx = reinterpret_cast<float*>(smem + Attn3Smem::OFF_MX);
-    float* const ls = reinterpret_cast<float*>(smem + Attn3Smem::OFF_LS);
-    float* const ms = reinterpret_cast<float*>(smem + Attn3Smem::OFF_MS);
-    uint8_t* const stage = smem + (t ? Attn3Smem::OFF_ST1 : Attn3Smem::OFF_ST0);
-    uint8_t* const xo = smem + Attn3Smem::OFF_ST1;
-    const bool store_thread = (hf == 0 && quad == 0 && lane == 0);
-    const bool tracer = (warp == 0 && lane == 0);
-    int k_blk = 0;           // key blocks this slot has processed so far (all items)
+    auto tid_now = []() {
+      uint32_t v;
+      asm volatile("mov.u32 %0, %%tid.x;" : "=r"(v));
+      return v;
+    };
+    // tid bits: [4:0] lane, [6:5] TMEM lane quadrant, [7] half of the block's key columns, [8] slot; row = tid & 127
+    auto tmem_s = [&](uint32_t tid) {  // this thread's first S column; P: + 128 - half * 32, O: + 192 - half * 32
+      return tmem_base + ((tid >> 8) & 1) * 256 + ((tid & 96u) << 16) + ((tid >> 7) & 1) * 64;
+    };
+    const uint32_t sb = smem_u32(smem);
+    const int t = warp >> 3;  // slot (warp-uniform)
+    int k_blk = 0;            // key blocks this slot has processed so far (all items)
     bool first_merge = true;
+    if (p.pingpong && t == 1) at3_bar_arrive(EXP_TURN, 512);  // slot 0 goes first
 #pragma unroll 1
     for (int idx = blockIdx.x; idx < geo.total; idx += G) {
-      const At3Item it = geo.item(idx, p.H);
-      const int ns = it.ns(t), jb = it.jb(t);
-      const float* const bb = p.bias ? p.bias + static_cast<long long>(it.b) * p.n : nullptr;
+      int ns, jb;
+      const float* bb;
+      {
+        const At3Item it = geo.item(idx, p.H);
+        ns = it.ns(t);
+        jb = it.jb(t);
+        bb = p.bias ? p.bias + static_cast<long long>(it.b) * p.n : nullptr;
+      }
       float m_run = -INFINITY;  // reference of the running sum / output (scaled log2 domain)
       float l_run = 0.0f;       // this half's partial row sum
 #pragma unroll 1
       for (int i = 0; i < ns; ++i, ++k_blk) {
-        const int j = jb + i;
-        const int kv_valid = min(AT3_BK, p.n - j * AT3_BK);
+        const int hf = (warp >> 2) & 1;
+        const int kv_valid = min(AT3_BK, p.n - (jb + i) * AT3_BK);
         const int hv16 = min(64, max(0, ((kv_valid + 15) & ~15) - hf * 64));  // columns of this half the PV MMA may read
         const int nchunk = (hv16 + 31) >> 5;
         const int lim0 = kv_valid - hf * 64;  // real keys in chunk 0 of this half (chunk 1: lim0 - 32); may be <= 0 or >= 32
         // key bias of this half's two chunks (lane = key), fetched before the wait; chunk-uniform path selection
         float bv0 = 0.0f, bv1 = 0.0f;
         if (bb) {
-          const int k0 = j * AT3_BK + hf * 64 + lane;
+          const int k0 = (jb + i) * AT3_BK + hf * 64 + lane;
           if (k0 < p.n) bv0 = __ldg(bb + k0) * ATT_LOG2E;
           if (k0 + 32 < p.n) bv1 = __ldg(bb + k0 + 32) * ATT_LOG2E;
         }
         const bool gen0 = __any_sync(0xffffffffu, bv0 != 0.0f) || lim0 < 32;
         const bool gen1 = __any_sync(0xffffffffu, bv1 != 0.0f) || lim0 < 64;
+        const float scale = p.scale_log2;
         uint32_t v[2][32], pk[16];
         mbar_wait_trap(&s_full[t], k_blk & 1);
         tc_fence_after();
-        if (tracer) TRACE_PT(0x500 + 0x10 + (k_blk & 15));  // s_full seen
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x10 + (k_blk & 15));  // s_full seen
         if (nchunk > 0) {
-          tmem_ld64(tS, v[0], v[1]);
+          tmem_ld64(tmem_s(tid_now()), v[0], v[1]);
           tmem_wait_ld_dep2(v[0], v[1]);
         }
         tc_fence_before();
@@ -476,14 +484,27 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         if (nchunk > 0) m_half = gen0 ? at3_chunk_max_m(v[0], scale, bv0, lim0) : at2_chunk_max<0>(v[0], scale, 0, 32) * scale;
         if (nchunk > 1)
           m_half = fmaxf(m_half, gen1 ? at3_chunk_max_m(v[1], scale, bv1, lim0 - 32) : at2_chunk_max<0>(v[1], scale, 0, 32) * scale);
-        float* const mxp = mx + (k_blk & 1) * 512 + t * 256;
-        mxp[hf * 128 + row] = m_half;
-        at3_bar_sync(pair_bar, 64);
-        const float m_blk = fmaxf(m_half, mxp[(hf ^ 1) * 128 + row]);
+        float m_blk;
+        {
+          // [2 parities][2 slots][2 halves][128 rows]; the other half of this row sits 512 bytes away (half bit = tid bit 7)
+          const uint32_t tid = tid_now();
+          const uint32_t own = sb + Attn3Smem::OFF_MX + (k_blk & 1) * 2048 + (tid & 511u) * 4;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(own), "f"(m_half) : "memory");
+          at3_bar_sync(1 + ((tid >> 8) & 1) * 4 + ((tid >> 5) & 3), 64);  // the two warps (halves) of this (slot, quadrant)
+          m_blk = fmaxf(m_half, lds_f32(own ^ 512u));
+        }
         const float ref = (m_blk > m_run + 8.0f) ? m_blk : m_run;  // m_run = -inf on the first block -> m_blk
         const float alpha = (ref == m_run) ? 1.0f : ex2_approx(m_run - ref);  // 0 on the first block
         const float neg_ref = -ref;
-        if (tracer) TRACE_PT(0x500 + 0x20 + (k_blk & 15));  // reference known
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x20 + (k_blk & 15));  // reference known
+        // The exponentials of the two slots take turns (token = named barriers EXP_TURN + slot; per-quadrant mbarrier
+        // tokens measured slower, 75.8 against 70.6 us: four more polling warps per scheduler): left alone the slots
+        // drift into phase, all four softmax warps of a scheduler then want the MUFU at the same time (a block's
+        // exponentials take 2300 cycles instead of 1024) and leave it idle together afterwards (in-kernel timeline,
+        // profiles/r02_attention.md).  In turns, one slot's exponentials run under the other slot's TMEM loads, maxima,
+        // sums, packs and P stores.
+        if (p.pingpong) at3_bar_sync(EXP_TURN + t, 512);
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x70 + (k_blk & 15));  // turn acquired
         // ---- exponentials (in place), then sums / packs / P stores; `p.zero` (always 0) gives ptxas a branch between
         //      the stages, i.e. separate scheduling regions (see at2_chunk_ex2) ----
         if (nchunk > 0) {
@@ -497,12 +518,17 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
           else if (VAR >= 2) at3_chunk_ex2_x2<NPOLY>(v[1], scale, neg_ref);
           else at2_chunk_ex2<0, VAR == 1>(v[1], scale, neg_ref, 0, 32);
         }
+        if (p.pingpong) at3_bar_arrive(EXP_TURN + (t ^ 1), 512);
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x80 + (k_blk & 15));  // exponentials done, turn passed
+        // slot 1 starts half a block behind slot 0 (see the MMA issuer)
+        if (k_blk == 0 && t == 0 && lane == 0) mbar_arrive(stagger);
         if (i > 0) {
           // P_t and O_t are free once PV_t of the previous block has drained (the exponentials were computed meanwhile)
           mbar_wait_trap(&pv_done[t], (k_blk - 1) & 1);
           tc_fence_after();
-          if (tracer) TRACE_PT(0x500 + 0x30 + (k_blk & 15));  // pv_done seen
+          if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x30 + (k_blk & 15));  // pv_done seen
           if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // bring this half's 32 output columns to the new reference (rare)
+            const uint32_t tO = tmem_s(tid_now()) + 192 - hf * 32;
 #pragma unroll 1
             for (int cc = 0; cc < 32; cc += 8) {
               uint32_t o[8];
@@ -517,12 +543,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         float l_blk = 0.0f;
         if (nchunk > 0) {
           l_blk += VAR >= 2 ? at3_chunk_sum_pack_x2(v[0], pk) : at2_chunk_sum_pack(v[0], pk);
-          tmem_st16(tP, pk);
+          tmem_st16(tmem_s(tid_now()) + 128 - hf * 32, pk);
         }
         if (p.zero) break;
         if (nchunk > 1) {
           l_blk += VAR >= 2 ? at3_chunk_sum_pack_x2(v[1], pk) : at2_chunk_sum_pack(v[1], pk);
-          tmem_st16(tP + 16, pk);
+          tmem_st16(tmem_s(tid_now()) + 128 - hf * 32 + 16, pk);
         }
         l_run = l_run * alpha + l_blk;
         m_run = ref;
@@ -530,89 +556,113 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
-        if (tracer) TRACE_PT(0x500 + 0x40 + (k_blk & 15));  // P stored
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x40 + (k_blk & 15));  // P stored
+      }
+      if (p.pingpong && t == 1) {
+        // slot 1 has fewer key blocks than slot 0 in a LONE item of an odd block count: pass the turns it does not use
+        const At3Item it1 = geo.item(idx, p.H);
+        for (int extra = it1.nsA - it1.nsB; extra > 0; --extra) {
+          at3_bar_sync(EXP_TURN + 1, 512);
+          at3_bar_arrive(EXP_TURN, 512);
+        }
       }
       if (ns == 0) continue;  // LONE item of a one-block sequence: slot 1 has nothing to do (and nothing to merge)
       // ---------------- item epilogue: O / l -> bf16 -> staging tile -> one TMA bulk store ----------------
       mbar_wait_trap(&pv_done[t], (k_blk - 1) & 1);
       tc_fence_after();
+      if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x61);  // last PV done
+      const uint32_t tid = tid_now();
+      const uint32_t hf = (tid >> 7) & 1, row = tid & 127u;
+      const bool store_thread = (tid & 255u) == 0;  // first thread of the slot
+      const int slot_bar = 9 + t;                    // the slot's 8 softmax warps
       if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free again
+      const At3Item it = geo.item(idx, p.H);
       const bool merge = it.lone && it.nsB > 0;
+      const uint32_t tO = tmem_s(tid) + 192 - hf * 32;
+      const uint32_t ls_row = sb + Attn3Smem::OFF_LS + row * 4;       // + (slot * 2 + half) * 512
+      const uint32_t xo = sb + Attn3Smem::OFF_ST1 + row * 16;         // + float4 index * 2048
       float inv_l, a_own = 1.0f, a_peer = 0.0f;
       if (!merge) {
-        ls[(t * 2 + hf) * 128 + row] = l_run;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ls_row + (t * 2 + hf) * 512), "f"(l_run) : "memory");
         at3_bar_sync(slot_bar, 256);
-        inv_l = 1.0f / (l_run + ls[(t * 2 + (hf ^ 1)) * 128 + row]);
+        if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x62);  // row sums exchanged
+        inv_l = 1.0f / (l_run + lds_f32(ls_row + (t * 2 + (hf ^ 1)) * 512));
       } else if (t == 1) {
         // slot 1 -> slot 0: chunk-major float4s (a warp writes 512 contiguous bytes per instruction)
         at3_bar_sync(slot_bar, 256);                       // slot 1's last TMA store has read the staging tile (= xo)
         if (!first_merge) at3_bar_sync(XO_FREE, 512);      // slot 0 has read the previous partial (xo, ms, ls)
         first_merge = false;
-        ls[(2 + hf) * 128 + row] = l_run;
-        if (hf == 0) ms[row] = m_run;
-        uint32_t o[32];
-        tmem_ld32(tO, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<uint4*>(xo + (((hf * 32 + q) >> 2) * AT3_BQ + row) * 16) = make_uint4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ls_row + (2 + hf) * 512), "f"(l_run) : "memory");
+        if (hf == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + Attn3Smem::OFF_MS + row * 4), "f"(m_run) : "memory");
+#pragma unroll 1
+        for (int q = 0; q < 32; q += 8) {
+          uint32_t o[8];
+          tmem_ld8(tO + q, o);
+          tmem_wait_ld();
+          sts128(xo + ((hf * 32 + q) >> 2) * 2048, __uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]),
+                 __uint_as_float(o[3]));
+          sts128(xo + (((hf * 32 + q) >> 2) + 1) * 2048, __uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]),
+                 __uint_as_float(o[7]));
+        }
         tc_fence_before();
         at3_bar_arrive(XO_FULL, 512);
         continue;  // slot 0 stores the tile
       } else {
-        ls[hf * 128 + row] = l_run;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ls_row + hf * 512), "f"(l_run) : "memory");
         at3_bar_sync(XO_FULL, 512);
-        const float m_peer = ms[row];
-        const float l_own = l_run + ls[(hf ^ 1) * 128 + row];
-        const float l_peer = ls[256 + row] + ls[384 + row];
+        const float m_peer = lds_f32(sb + Attn3Smem::OFF_MS + row * 4);
+        const float l_own = l_run + lds_f32(ls_row + (hf ^ 1) * 512);
+        const float l_peer = lds_f32(ls_row + 2 * 512) + lds_f32(ls_row + 3 * 512);
         const float m = fmaxf(m_run, m_peer);
         a_own = ex2_approx(m_run - m);
         a_peer = ex2_approx(m_peer - m);
         inv_l = 1.0f / (l_own * a_own + l_peer * a_peer);
       }
       {
-        uint32_t o[32];
-        tmem_ld32(tO, o);
-        tmem_wait_ld();
-        if (merge) {
-#pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 x = *reinterpret_cast<const float4*>(xo + (((hf * 32 + q) >> 2) * AT3_BQ + row) * 16);
-            o[q] = __float_as_uint(__uint_as_float(o[q]) * a_own + x.x * a_peer);
-            o[q + 1] = __float_as_uint(__uint_as_float(o[q + 1]) * a_own + x.y * a_peer);
-            o[q + 2] = __float_as_uint(__uint_as_float(o[q + 2]) * a_own + x.z * a_peer);
-            o[q + 3] = __float_as_uint(__uint_as_float(o[q + 3]) * a_own + x.w * a_peer);
-          }
-          at3_bar_arrive(XO_FREE, 512);  // slot 1 may overwrite its partial
-        }
+        // 8 output columns at a time (one 16-byte chunk of the bf16 row): the epilogue keeps few registers live.
         // bf16 row -> staging tile, 16-byte chunks XOR-swizzled with row % 8: that IS the 128B-swizzle TMA layout, and
         // the writes are bank-conflict free
-        uint8_t* const st_row = stage + row * 128;
+        const uint32_t st_row = sb + (t ? Attn3Smem::OFF_ST1 : Attn3Smem::OFF_ST0) + row * 128;
+        a_own *= inv_l;
+        a_peer *= inv_l;
 #pragma unroll
         for (int q = 0; q < 32; q += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[q]) * inv_l, __uint_as_float(o[q + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[q + 2]) * inv_l, __uint_as_float(o[q + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[q + 4]) * inv_l, __uint_as_float(o[q + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[q + 6]) * inv_l, __uint_as_float(o[q + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(st_row + ((((hf * 32 + q) >> 3) ^ (row & 7)) << 4)) = u;
+          uint32_t o[8];
+          tmem_ld8(tO + q, o);
+          tmem_wait_ld();
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[e]) * a_own;
+          if (merge) {
+            const float4 x0 = lds128(xo + ((hf * 32 + q) >> 2) * 2048), x1 = lds128(xo + (((hf * 32 + q) >> 2) + 1) * 2048);
+            f[0] += x0.x * a_peer; f[1] += x0.y * a_peer; f[2] += x0.z * a_peer; f[3] += x0.w * a_peer;
+            f[4] += x1.x * a_peer; f[5] += x1.y * a_peer; f[6] += x1.z * a_peer; f[7] += x1.w * a_peer;
+          }
+          sts128(st_row + ((((hf * 32 + q) >> 3) ^ (row & 7)) << 4), __uint_as_float(pack_bf16x2(f[0], f[1])),
+                 __uint_as_float(pack_bf16x2(f[2], f[3])), __uint_as_float(pack_bf16x2(f[4], f[5])),
+                 __uint_as_float(pack_bf16x2(f[6], f[7])));
         }
+        if (merge) at3_bar_arrive(XO_FREE, 512);  // slot 1 may overwrite its partial
       }
+      if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x63);  // staging rows written
       tc_fence_before();         // this item's TMEM reads are ordered before the p_full arrive of the next item's first block
       fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the TMA (async proxy)
+      if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x64);  // fenced
       at3_bar_sync(slot_bar, 256);
+      if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x65);  // slot barrier passed
       if (store_thread) {
         // rows >= n are clipped by the tensor map
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                          reinterpret_cast<uint64_t>(&tma_out)),
-                     "r"(smem_u32(stage)), "r"(it.h * ATT_D), "r"(it.q0(t)), "r"(it.b)
+                     "r"(sb + (t ? Attn3Smem::OFF_ST1 : Attn3Smem::OFF_ST0)), "r"(it.h * ATT_D), "r"(it.q0(t)), "r"(it.b)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      if (tracer) TRACE_PT(0x500 + 0x60);  // item stored
+      if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x60);  // item stored
     }
-    if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes are complete before the CTA exits
+    if ((tid_now() & 255u) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the writes are complete before the CTA exits
     tc_fence_before();
+    const bool tracer = (warp == 0 && lane == 0);
     if (tracer) TRACE_FLUSH();
   }
 

@@ -86,16 +86,25 @@ static int g_attn_split = [] {
   return (e && e[0] == '0') ? 0 : 1;
 }();
 
-// UVLT_ATTN_V=2 selects the second-generation attention kernel (attention2.cuh: P in tensor memory, two slots per CTA).
-// Measured on B200 (tools/kernel_sweep.py attn, profiles/r02_attention.md), us per launch, v1 / v2:
-//   B=32: n=553 77.1 / 92.4, n=513 73.2 / 88.4, n=361 35.5 / 50.9      B=8: n=553 26.8 / 24.5, n=361 13.8 / 17.2
-//   B=1:  n=553 8.4 / 8.2, n=513 7.7 / 8.2, n=361 7.4 / 6.6
-// v1 (three CTAs per SM, 64-key blocks) hides its per-block latency chain across CTAs and stays the default; v2 is one
-// CTA per SM and pays ~8k cycles of set-up / drain per CTA that a persistent work loop would hide (next step).
-// UVLT_ATTN_POLY=1: a quarter of v2's exponentials on the FMA pipe (no gain while the kernel is not MUFU bound).
+// Attention kernel selection.  Default (UVLT_ATTN_V unset or 0): the third-generation kernel (attention3.cuh: persistent
+// CTAs, two threads per query row, P in tensor memory) for large grids of mid-length sequences, the first kernel
+// (attention.cuh, three CTAs per SM, 64-key blocks; its key-split cluster variant for small grids) everywhere else.
+// UVLT_ATTN_V=1 / 2 / 3 forces one generation (2 = attention2.cuh, the one-CTA-per-SM predecessor of 3; 3 still leaves
+// small grids to the key-split variant unless UVLT_ATTN_SPLIT=0).
+// Measured on B200 (tools/kernel_sweep.py attn, profiles/r02_attention.md), us per launch, v1 / v3:
+//   H=12: B=32 n=553 76.6 / 70.0, n=513 72.7 / 68.2, n=361 35.3 / 35.0   B=16 n=553 41.9 / 36.9   B=8 n=553 26.8 / 22.3
+//         B=4 n=553 18.7 / 13.4
+//   H=16 (UVLTrack-L): B=8 n=1193 89.9 / 89.3, B=4 51.9 / 54.6, B=2 32.2 / 37.6 (few work items per CTA: tail imbalance)
+// UVLT_ATTN_POLY: softmax arithmetic variant of v3 (0..5, attention3.cuh; default 2 = packed FFMA2 / FADD2, every
+// exponential on the MUFU), or for v2 1 = a quarter of the exponentials on the FMA pipe.
 static int g_attn_v = [] {
   const char* e = getenv("UVLT_ATTN_V");
-  return (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : 1;
+  return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;  // 0 = automatic
+}();
+// UVLT_ATTN_PINGPONG=0: the two slots of the third-generation kernel do not take turns on the MUFU (A/B timing)
+static int g_attn_pingpong = [] {
+  const char* e = getenv("UVLT_ATTN_PINGPONG");
+  return (e && e[0] == '0') ? 0 : 1;
 }();
 // UVLT_ATTN_GRID=<n> caps the persistent grid of the third-generation kernel (tests: many work items per CTA)
 static int g_attn_grid_cap = [] {
@@ -104,7 +113,7 @@ static int g_attn_grid_cap = [] {
 }();
 static int g_attn_poly = [] {
   const char* e = getenv("UVLT_ATTN_POLY");
-  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh)
+  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh); -1 = default
 }();
 
 // cudaFuncSetAttribute applies to the CURRENT device: the opt-in is tracked per device ordinal, so a process that creates
@@ -158,7 +167,7 @@ int init_kernel_attributes() {
 // L2 bandwidth and only adds the cross-CTA slot handshake.  UVLT_MULTICAST=1 enables it for experiments.
 int g_gemm_multicast = [] {
   const char* e = getenv("UVLT_MULTICAST");
-  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh)
+  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh); -1 = default
 }();
 
 // CTA-pair persistent GEMM (gemm_bf16_tn_2sm_kernel): UVLT_GEMM_2SM=0 never, 1 by the rule below (default), 2 wherever
@@ -418,7 +427,7 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   a->split = g_attn_split && cb * H * ((n + ATT_BQ - 1) / ATT_BQ) <= g_num_sms && (n + ATT_BKV - 1) / ATT_BKV >= 2;
   a->v2 = g_attn_v == 2;
   a->poly = g_attn_poly == 1;
-  a->var3 = g_attn_poly <= 5 ? g_attn_poly : 0;
+  a->var3 = (g_attn_poly >= 0 && g_attn_poly <= 5) ? g_attn_poly : 2;
   a->p2.n = n;
   a->p2.H = H;
   a->p2.scale_log2 = a->p.scale_log2;
@@ -436,7 +445,8 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   {
     const int ntiles = (n + AT3_BQ - 1) / AT3_BQ;
     const int items = B * H * ((ntiles >> 1) + (ntiles & 1));
-    a->v3 = g_attn_v == 3 && !a->split;
+    // automatic: where v3 measured faster (table above): grids beyond one CTA per SM, four or five query tiles
+    a->v3 = !a->split && (g_attn_v == 3 || (g_attn_v == 0 && n > 384 && n <= 640));
     a->grid3 = items < g_num_sms ? items : g_num_sms;
     if (g_attn_grid_cap > 0 && a->grid3 > g_attn_grid_cap) a->grid3 = g_attn_grid_cap;
     a->p3.n = n;
@@ -445,6 +455,7 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
     a->p3.scale_log2 = a->p.scale_log2;
     a->p3.bias = bias;
     a->p3.zero = 0;
+    a->p3.pingpong = g_attn_pingpong;
   }
   return 0;
 }

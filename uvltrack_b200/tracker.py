@@ -24,6 +24,39 @@ from .misc import NestedTensor
 from .model import build_model
 
 
+class PinnedFrame(np.ndarray):
+    """A video frame that lives in page-locked host memory (made by :func:`pinned_frames`).  ``BatchTracker.track``
+    uploads such frames straight from where they are -- no copy into a staging buffer, no host thread touching the
+    pixels -- so the per-frame host cost of a sequence no longer grows with the frame size (with 8 ranks on one host the
+    pageable -> pinned staging copies of 8 x 32 frames per step saturated the host's cores, SCALE run of round 2)."""
+
+
+def pinned_frames(frames):
+    """Frames (uint8 [H, W, 3] arrays of one size, e.g. a decoded video) -> the same pixels in ONE page-locked block,
+    returned as a list of :class:`PinnedFrame` views.  This is what a video reader does once per clip (or what a decoder
+    writing into page-locked buffers does for free); the tracker then streams the frames to the GPU with asynchronous
+    copies only.  The buffers must stay unmodified until the ``track`` call AFTER the one they were passed to as
+    ``next_images`` has returned."""
+    import torch
+
+    frames = list(frames)
+    if not frames:
+        return []
+    a0 = np.asarray(frames[0])
+    if a0.dtype != np.uint8 or a0.ndim != 3 or any(np.asarray(f).shape != a0.shape for f in frames):
+        raise ValueError("pinned_frames: uint8 [H, W, 3] frames of one size expected")
+    block = torch.empty((len(frames),) + a0.shape, dtype=torch.uint8, pin_memory=True)
+    base = block.numpy()  # keeps the tensor's storage alive for as long as any view of it exists
+    for i, f in enumerate(frames):
+        base[i] = f
+    view = base.view(PinnedFrame)
+    return [view[i] for i in range(len(frames))]
+
+
+def _all_pinned(images) -> bool:
+    return all(isinstance(im, PinnedFrame) and im.flags.c_contiguous for im in images)
+
+
 def _is_whitespace(ch: str) -> bool:
     return ch in " \t\n\r" or unicodedata.category(ch) == "Zs"
 
@@ -374,6 +407,17 @@ class BatchTracker:
                 raise RuntimeError("uvlt_upload_frames_slot failed")
         return (b1 - b0) * per
 
+    def _prefetch_pinned(self, images, slot, per):
+        """Double buffering without staging: the next step's frames are page-locked already (PinnedFrame), so the worker
+        thread only enqueues B asynchronous copies on the copy stream; no host thread reads a pixel."""
+        lib, h = self.engine.lib, self.engine.h
+        total = self.B * per
+        stream = self._pf_stream.cuda_stream
+        for b, im in enumerate(images):
+            if lib.uvlt_upload_frames_slot(h, im.ctypes.data, b * per, per, total, slot, stream):
+                raise RuntimeError("uvlt_upload_frames_slot failed")
+        return total
+
     def track(self, images, raise_on_failure: bool = True, next_images=None):
         """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch.
 
@@ -436,6 +480,7 @@ class BatchTracker:
 
             factor = float(self.params.search_factor)
             pitch = W * 3
+            src_pinned = (not prefetched) and _all_pinned(images)
 
             def stage(b):
                 # only the search window of the frame is read by sample_target (processing_utils.py:183-199): stage and
@@ -444,9 +489,13 @@ class BatchTracker:
                 if win is None:
                     return 0  # window entirely outside the frame (the crop is all padding) or a degenerate box
                 xa, ya, xb, yb = win
-                np.copyto(self.frames_np[b, ya:yb, xa:xb], images[b][ya:yb, xa:xb])
                 off = b * per + ya * pitch + xa * 3
-                if lib.uvlt_upload_frames_2d(h, f["frames_ptr"] + off, pitch, off, pitch, (xb - xa) * 3, yb - ya,
+                if src_pinned:  # page-locked source: the DMA reads the window where it is
+                    src = images[b].ctypes.data + ya * pitch + xa * 3
+                else:
+                    np.copyto(self.frames_np[b, ya:yb, xa:xb], images[b][ya:yb, xa:xb])
+                    src = f["frames_ptr"] + off
+                if lib.uvlt_upload_frames_2d(h, src, pitch, off, pitch, (xb - xa) * 3, yb - ya,
                                              f["total"], stream):
                     raise RuntimeError("uvlt_upload_frames_2d failed")
                 return (xb - xa) * 3 * (yb - ya)
@@ -460,17 +509,20 @@ class BatchTracker:
             if next_images is not None and len(next_images) == self.B and all(
                     im.shape == images[0].shape and im.dtype == np.uint8 for im in next_images):
                 nslot = 1 - use_slot
-                if self._pf_frames[nslot] is None or tuple(self._pf_frames[nslot].shape[1:3]) != (H, W):
-                    self._pf_frames[nslot] = torch.empty(self.B, H, W, 3, dtype=torch.uint8, pin_memory=True)
-                    self._pf_np[nslot] = self._pf_frames[nslot].numpy()
                 if self._pf_stream is None:
                     self._pf_stream = torch.cuda.Stream()
                     self._pf_events = [torch.cuda.Event(), torch.cuda.Event()]
                 nxt = list(next_images)
-                njobs = min(4, self.B)
-                cuts = [self.B * k // njobs for k in range(njobs + 1)]
-                self._pf_pending = ([self._pool.submit(self._prefetch_job, nxt, nslot, H, W, cuts[k], cuts[k + 1])
-                                     for k in range(njobs)], nxt, nslot, (H, W))
+                if _all_pinned(nxt):
+                    self._pf_pending = ([self._pool.submit(self._prefetch_pinned, nxt, nslot, per)], nxt, nslot, (H, W))
+                else:
+                    if self._pf_frames[nslot] is None or tuple(self._pf_frames[nslot].shape[1:3]) != (H, W):
+                        self._pf_frames[nslot] = torch.empty(self.B, H, W, 3, dtype=torch.uint8, pin_memory=True)
+                        self._pf_np[nslot] = self._pf_frames[nslot].numpy()
+                    njobs = min(4, self.B)
+                    cuts = [self.B * k // njobs for k in range(njobs + 1)]
+                    self._pf_pending = ([self._pool.submit(self._prefetch_job, nxt, nslot, H, W, cuts[k], cuts[k + 1])
+                                         for k in range(njobs)], nxt, nslot, (H, W))
             t_staged = time.perf_counter()
             rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
                                                  f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
