@@ -53,6 +53,16 @@ def pinned_frames(frames):
     return [view[i] for i in range(len(frames))]
 
 
+class _Done:
+    """A finished job with the ``result()`` of a future."""
+
+    def __init__(self, value):
+        self._value = value
+
+    def result(self):
+        return self._value
+
+
 def _all_pinned(images) -> bool:
     return all(isinstance(im, PinnedFrame) and im.flags.c_contiguous for im in images)
 
@@ -376,8 +386,29 @@ class BatchTracker:
             self.engine.text_encode(text, self.flag)
             self.engine._text_owner = self  # the cache lives in the engine: another tracker on it may overwrite it
         self.prompt.copy_(self.network.forward_prompt_init(self.template, ctx, text, self.template_mask, ctx_mask, self.flag))
+        if self.has_cont:
+            self._apply_prompt_update([0], np.zeros((self.B, d.nx), dtype=np.uint8), dry_run=True)
         self.frame_id = 0
         torch.cuda.synchronize()
+
+    def _apply_prompt_update(self, update, cm, dry_run=False):
+        """Device half of the prompt update (lib/test/tracker/uvltrack.py:127-136): new prompts for the sequences in
+        ``update`` from the best-frame snapshot and their context masks ``cm``.  ``dry_run`` runs every operation but
+        writes the old values back: initialize() uses it once so that the first real update -- which falls inside a
+        sequence, and inside bench.py's timed region on the ranks whose scores cross the threshold -- does not pay the
+        first-use cost of the indexing kernels (lazy module loading: ~16 ms measured on the 8-GPU run of round 2)."""
+        import torch
+
+        new_prompt = self.engine.forward_prompt(self.snapshot, self.flag, self.template_mask,
+                                                torch.from_numpy(cm).cuda(), self.text_mask)
+        sel = torch.tensor(update, device="cuda")
+        if dry_run:
+            new_prompt = self.prompt.clone()
+            self.prompt[sel] = new_prompt[sel]
+            self.max_score_dev[sel] = self.max_score_dev[sel] * 1
+        else:
+            self.prompt[sel] = new_prompt[sel]
+            self.max_score_dev[sel] = 0
 
     def _bind_fast_path(self, H, W):
         """Raw device / pinned pointers of everything the per-frame call takes (the tensors are allocated once in
@@ -514,7 +545,10 @@ class BatchTracker:
                     self._pf_events = [torch.cuda.Event(), torch.cuda.Event()]
                 nxt = list(next_images)
                 if _all_pinned(nxt):
-                    self._pf_pending = ([self._pool.submit(self._prefetch_pinned, nxt, nslot, per)], nxt, nslot, (H, W))
+                    if self.B <= 4:  # a few enqueue-only calls: cheaper inline than a hand-over to the worker thread
+                        self._pf_pending = ([_Done(self._prefetch_pinned(nxt, nslot, per))], nxt, nslot, (H, W))
+                    else:
+                        self._pf_pending = ([self._pool.submit(self._prefetch_pinned, nxt, nslot, per)], nxt, nslot, (H, W))
                 else:
                     if self._pf_frames[nslot] is None or tuple(self._pf_frames[nslot].shape[1:3]) != (H, W):
                         self._pf_frames[nslot] = torch.empty(self.B, H, W, 3, dtype=torch.uint8, pin_memory=True)
@@ -592,11 +626,7 @@ class BatchTracker:
             for b in update:
                 cx, cy, w, h = self.pred_box_net[b]
                 cm[b] = pp.anno2mask(np.array([[cx - 0.5 * w, cy - 0.5 * h, w, h]], dtype=np.float32), S // 16)[0]
-            new_prompt = self.engine.forward_prompt(self.snapshot, self.flag, self.template_mask,
-                                                    torch.from_numpy(cm).cuda(), self.text_mask)
-            sel = torch.tensor(update, device="cuda")
-            self.prompt[sel] = new_prompt[sel]
-            self.max_score_dev[sel] = 0
+            self._apply_prompt_update(update, cm)
             for b in update:
                 self.max_score[b] = 0.0
         t_end = time.perf_counter()
