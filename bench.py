@@ -605,17 +605,17 @@ def run_b200(a):
     attach_rooflines(prim, a.batch, pk, "b%d" % a.batch)
     for key, w in extra.items():
         attach_rooflines(w, w["sequences_per_gpu"], pk, "b32" if w["sequences_per_gpu"] == 32 else "l8")
-    cfgd = primary_config(a, world, prim["text_branch_cached_per_sequence"])
-    cfgd.update({"skip_dead_text_branch": prim["skip_dead_text_branch"],
-                 "text_branch_cached_per_sequence": prim["text_branch_cached_per_sequence"],
-                 "vs_baseline_note": "value / 60 FPS = the reference's RTX-3090 profile_model.py figure for UVLTrack-B "
-                                     "(z128/x256, forward_test only); this workload is the heavier 256/256 shape"})
+    cfgd = primary_config(a, world, prim["text_branch_cached_per_sequence"])  # identical in both arms (driver: same_config)
+    impl_notes = {"skip_dead_text_branch": prim["skip_dead_text_branch"],
+                  "text_branch_cached_per_sequence": prim["text_branch_cached_per_sequence"],
+                  "vs_baseline_note": "value / 60 FPS = the reference's RTX-3090 profile_model.py figure for UVLTrack-B "
+                                      "(z128/x256, forward_test only); this workload is the heavier 256/256 shape"}
     line = {
         "metric": "tracker FPS (frames/sec)", "value": prim["value"], "unit": "frames/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": prim["ms_per_step"],
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": round(prim["value"] / world / BASELINE_FPS_3090, 2) if (a.arch == "base" and a.batch == 1) else None,
-        "dtype": "bf16", "data": "synthetic", "config": cfgd,
+        "dtype": "bf16", "data": "synthetic", "config": cfgd, "implementation": impl_notes,
         "e2e": dict(prim["e2e"], frames="pageable numpy arrays, staged into pinned memory by host threads" if a.pageable_frames
                     else "page-locked host memory (uvltrack_b200.tracker.pinned_frames), copied by DMA only",
                     path="BatchTracker.track(): raw uint8 frames (480x640x3) in host memory -> whole frames of the NEXT step "

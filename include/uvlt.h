@@ -244,6 +244,13 @@ UVLT_API int uvlt_last_launch_count(uvlt_handle h);
  * B200 measurements (profiles/r01_gemm_2sm.md, tools/kernel_sweep.py); tests/test_host_logic.py pins them. */
 UVLT_API int uvlt_gemm_plan(int M, int N, int K, int groups, int out_f32, int act, int split_k, int32_t* plan);
 
+/* Host-only query: the process-wide kernel switches as the library resolved them from the environment (UVLT_PDL,
+ * UVLT_MULTICAST, UVLT_GEMM_2SM, UVLT_ATTN_V, UVLT_ATTN_SPLIT, UVLT_ATTN_POLY).  out[0..5] = programmatic dependent
+ * launch on, TMA-multicast GEMM variant on, CTA-pair GEMM mode (0 never / 1 by rule / 2 forced), attention generation
+ * (0 = automatic), key-split attention on, softmax variant of the third-generation kernel.  The defaults are the
+ * measured-best configuration; tests/test_host_logic.py pins them (a default that flips silently costs 6 % at batch 1). */
+UVLT_API int uvlt_runtime_switches(int32_t* out6);
+
 /* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + resid;  A, W bf16 row-major; bias fp32 [N] or NULL; resid fp32 [M,N]
  * or NULL (may alias out when out_f32); out bf16 or fp32.  nn.Linear semantics (block.py:49,59; utils.py:63-69).
  * bn: tile width 32/64/128/256, 0 = auto, 512 = the CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tile per pair of

@@ -199,3 +199,24 @@ def test_gemm_planner_rules_are_pinned():
     assert plan(4 * n, 2304, 768)[0] == 0 and plan(32 * 256, 128, 2304, 0, 2, 0, groups=4)[0] == 0
     assert plan(32 * n, 320, 768)[0] == 0
     assert lib.uvlt_gemm_plan(0, 8, 8, 1, 0, 0, 0, p) != 0
+
+
+def test_runtime_switch_defaults_are_pinned():
+    """The kernel switches resolved from the environment must default to the measured-best configuration (DESIGN.md
+    section 4): PDL on, TMA-multicast GEMM off (10-25 % slower at M = 513), CTA-pair GEMM by rule, automatic attention
+    generation, key-split attention on, packed-arithmetic softmax.  Run in a subprocess with the UVLT_* variables removed
+    (the switches are read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import ctypes as C; from uvltrack_b200 import _cabi; lib = _cabi.load(); o = (C.c_int32 * 6)(); "
+            "assert lib.uvlt_runtime_switches(o) == 0; print(list(o))")
+    env = {k: v for k, v in os.environ.items() if not k.startswith("UVLT_")}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == "[1, 0, 1, 0, 1, 2]"
+    r = subprocess.run([sys.executable, "-c", code], env=dict(env, UVLT_MULTICAST="1", UVLT_ATTN_V="3", UVLT_ATTN_POLY="4"),
+                       capture_output=True, text=True, cwd=root)
+    assert r.stdout.strip().splitlines()[-1] == "[1, 1, 1, 3, 1, 4]"

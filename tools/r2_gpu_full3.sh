@@ -9,6 +9,7 @@ grep -E "^===|rc=|passed|failed|Error" $L | cut -c1-200
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/r2_full3_bench.json').read().strip().splitlines()[-1])
-print('B1', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_phases_ms_per_step'], d['roofline_attention']['avg_launch_us'])
-for k,v in d['configs'].items(): print(k, v['value'], v['ms_per_step'], v['e2e']['value'], v['roofline_attention']['avg_launch_us'], v['roofline_attention']['frac'], v['roofline']['frac'])
+print('B1', d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_phases_ms_per_step'], d['roofline_attention']['avg_launch_us'], d['roofline']['per_shape'])
+for k,v in d['configs'].items(): print(k, v['value'], v['ms_per_step'], v['e2e']['value'], v['roofline_attention']['avg_launch_us'], v['roofline_attention']['frac'], v['roofline']['frac'], v['roofline']['per_shape'])
 PY
+bash tools/r2_gpu_sanitize3.sh

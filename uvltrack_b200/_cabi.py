@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuvlt_sm100.so")
+# UVLT_LIB: another build of the same C ABI (A/B timing of two library builds on one box, tools/r2_gpu_ab.sh)
+LIB_PATH = os.environ.get("UVLT_LIB") or os.path.join(_HERE, "libuvlt_sm100.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -76,6 +77,7 @@ SIGNATURES = {
     "uvlt_last_launch_count": (c_int, [c_void_p]),
     "uvlt_op_gemm": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "uvlt_gemm_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_int32)]),
+    "uvlt_runtime_switches": (c_int, [C.POINTER(c_int32)]),
     "uvlt_op_gemm_splitk": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, C.POINTER(c_int), _P]),
     "uvlt_op_gemm_grouped": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_longlong, c_longlong,
                                      c_int, _P]),

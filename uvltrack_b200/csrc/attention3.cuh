@@ -153,18 +153,6 @@ __device__ __forceinline__ void at3_chunk_ex2_m(uint32_t (&v)[32], float scale, 
 
 // ---- packed fp32 pairs (FFMA2 / FADD2, sm_100): half the FMA-pipe issue slots of the scale-and-subtract and of the row
 //      sums; the 64 scores of a thread arrive from tcgen05.ld in consecutive registers, so (2i, 2i+1) are aligned pairs ----
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
 // 2^x for a pair on the FMA pipe (same Cody-Waite split and degree-3 polynomial as ex2_poly3 in attention2.cuh)
 __device__ __forceinline__ void ex2_poly3_x2(float& y0, float& y1, float x0, float x1) {
   x0 = fmaxf(x0, -125.0f);

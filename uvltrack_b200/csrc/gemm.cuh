@@ -94,7 +94,8 @@ enum { EPI_BF16 = 0, EPI_BF16_GELU = 1, EPI_BF16_RELU = 2, EPI_F32 = 3 };
 //                (same-row in-place residual, or a periodic table such as the positional embedding)
 
 __device__ __forceinline__ float4 gelu4(float4 v) {
-  v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+  gelu_erf_x2(v.x, v.y);
+  gelu_erf_x2(v.z, v.w);
   return v;
 }
 

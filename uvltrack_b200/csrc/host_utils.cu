@@ -147,11 +147,7 @@ int init_kernel_attributes() {
                                     AttnSmem::TOTAL_SPLIT));
   UVLT_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::TOTAL));
-#define UVLT_AT3_ATTR(VAR) \
-  UVLT_CUDA_OK(cudaFuncSetAttribute(attention3_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Smem::TOTAL))
-  UVLT_AT3_ATTR(0); UVLT_AT3_ATTR(1); UVLT_AT3_ATTR(2); UVLT_AT3_ATTR(3); UVLT_AT3_ATTR(4); UVLT_AT3_ATTR(5);
+  if (attn23_init_attributes()) return 1;  // attention_big.cu
   {
     int dev = 0, sms = 0;
     UVLT_CUDA_OK(cudaGetDevice(&dev));
@@ -167,7 +163,7 @@ int init_kernel_attributes() {
 // L2 bandwidth and only adds the cross-CTA slot handshake.  UVLT_MULTICAST=1 enables it for experiments.
 int g_gemm_multicast = [] {
   const char* e = getenv("UVLT_MULTICAST");
-  return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1;  // v2: 0 / 1; v3: variant 0..5 (attention3.cuh); -1 = default
+  return (e && e[0] == '1') ? 1 : 0;
 }();
 
 // CTA-pair persistent GEMM (gemm_bf16_tn_2sm_kernel): UVLT_GEMM_2SM=0 never, 1 by the rule below (default), 2 wherever
@@ -460,29 +456,17 @@ int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const floa
   return 0;
 }
 
+void runtime_switches(int32_t* out6) {
+  out6[0] = g_pdl_enabled;
+  out6[1] = g_gemm_multicast;
+  out6[2] = g_gemm_2sm;
+  out6[3] = g_attn_v;
+  out6[4] = g_attn_split;
+  out6[5] = (g_attn_poly >= 0 && g_attn_poly <= 5) ? g_attn_poly : 2;
+}
+
 int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
-  if (a.v3) {
-#define UVLT_AT3_LAUNCH(VAR) \
-  UVLT_LAUNCH(attention3_kernel<VAR>, dim3(a.grid3), dim3(AT3_THREADS), Attn3Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p3)
-    switch (a.var3) {
-      case 1: UVLT_AT3_LAUNCH(1); break;
-      case 2: UVLT_AT3_LAUNCH(2); break;
-      case 3: UVLT_AT3_LAUNCH(3); break;
-      case 4: UVLT_AT3_LAUNCH(4); break;
-      case 5: UVLT_AT3_LAUNCH(5); break;
-      default: UVLT_AT3_LAUNCH(0); break;
-    }
-    UVLT_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
-  if (a.v2) {
-    const int ntiles = (a.p2.n + AT2_BQ - 1) / AT2_BQ;
-    dim3 grid2(a.p2.split_all ? ntiles : (ntiles + 1) / 2, a.p2.H, a.B);
-    if (a.poly) UVLT_LAUNCH(attention2_kernel<true>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p2);
-    else UVLT_LAUNCH(attention2_kernel<false>, grid2, dim3(AT2_THREADS), Attn2Smem::TOTAL, stream, a.tma_qkv, a.tma_o, a.p2);
-    UVLT_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
+  if (a.v3 || a.v2) return attn23_launch(a, stream);  // attention_big.cu
   dim3 grid((a.p.n + ATT_BQ - 1) / ATT_BQ, a.p.H, a.B);
   if (a.split) {
     grid.x *= 2;
@@ -498,6 +482,7 @@ int attn_launch(const AttnLaunch& a, cudaStream_t stream) {
 }  // namespace uvlt
 
 #ifdef UVLT_TRACE
+#include "attention_big.cu"  // trace builds: one module, one g_trace buffer
 // debug builds only (make TRACE=1): copy out and reset the in-kernel timeline; out = [n][3] uint64 (tag, clk, ns)
 extern "C" __attribute__((visibility("default"))) int uvlt_debug_trace(unsigned long long* out, int max_recs) {
   cudaDeviceSynchronize();

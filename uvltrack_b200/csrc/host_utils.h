@@ -91,7 +91,11 @@ struct AttnLaunch {
 int attn_prepare(AttnLaunch* a, const void* qkv, int B, int n, int H, const float* bias, void* out, const void* vt,
                  int n_pad, int capacity_batch = 0);
 int attn_launch(const AttnLaunch& a, cudaStream_t stream);
+// the second- and third-generation kernels live in their own translation unit (attention_big.cu), see there
+int attn23_init_attributes();
+int attn23_launch(const AttnLaunch& a, cudaStream_t stream);
 
+void runtime_switches(int32_t* out6);  // see uvlt_runtime_switches (include/uvlt.h)
 int init_kernel_attributes();  // cudaFuncSetAttribute(max dynamic smem) for every instantiation; idempotent
 
 }  // namespace uvlt

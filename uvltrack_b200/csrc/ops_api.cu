@@ -66,6 +66,12 @@ int uvlt_gemm_plan(int M, int N, int K, int groups, int out_f32, int act, int sp
   return 0;
 }
 
+int uvlt_runtime_switches(int32_t* out6) {
+  if (!out6) return 1;
+  runtime_switches(out6);
+  return 0;
+}
+
 int uvlt_op_gemm_grouped(const void* A, const void* W, const float* bias, void* out, int groups, int M, int N, int K,
                          int act, long long out_ld, long long out_gstride, int bn, void* stream) {
   if (init_kernel_attributes()) return 1;
