@@ -487,7 +487,9 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
         tracker.engine._text_owner = None  # the device-resident loop overwrote the engine's text cache
     frames_at = lambda t: [s[0][t] for s in seqs]  # noqa: E731
     for t_ in range(1, warmup + 1):
-        tracker.track(frames_at(t_), next_images=frames_at(t_ + 1))
+        # the last warm-up step neither prefetches nor commits its successor: no copy and no kernel of a timed step starts
+        # before the timed region
+        tracker.track(frames_at(t_), next_images=frames_at(t_ + 1) if t_ < warmup else None, commit_next=t_ < warmup)
     traj = np.zeros((B, steps, 4), dtype=np.float32)
     traj_dev = torch.zeros(B, steps, 4, device="cuda")
     dp.warmup_gather(traj_dev)  # NCCL builds its communicator lazily: not part of the run
@@ -501,7 +503,10 @@ def measure_workload(arch, z, x, mode, B, steps, warmup, rank, world, pk, with_r
     for i in range(steps):
         # the caller knows its next frames (a video file, a camera queue): they are staged and uploaded while this
         # step computes (double-buffered frame staging); every copy is still inside the timed region
-        res = tracker.track(frames_at(warmup + 1 + i), next_images=frames_at(warmup + 2 + i) if i + 1 < steps else None)
+        # ... and it commits to them (commit_next): step i + 1 is enqueued before this call returns, so the GPU does not idle
+        # while the host turns the rows of step i into results
+        res = tracker.track(frames_at(warmup + 1 + i), next_images=frames_at(warmup + 2 + i) if i + 1 < steps else None,
+                            commit_next=True)
         e2e_launches += eng.last_launch_count
         for b in range(B):
             traj[b, i] = res[b]["target_bbox"]

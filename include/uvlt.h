@@ -104,6 +104,11 @@ typedef struct uvlt_outputs {
 #define UVLT_FRAME_SLOT1 8 /* uvlt_track_frame_image_host: crop from frame-staging slot 1 (filled with
                               uvlt_upload_frames_slot) instead of slot 0 */
 
+#define UVLT_NO_SYNC 16    /* uvlt_track_frame_image_host: enqueue the step (incl. the copy of the result rows to out_host,
+                              which must then be page-locked) and return without synchronising the stream; the caller
+                              waits with uvlt_step_wait (or uvlt_stream_sync) before it reads out_host.  Lets a caller that knows its next
+                              frames launch step t+1 before it post-processes the rows of step t. */
+
 #define UVLT_TEXT_CACHED 4 /* the text rows entering the first fusion layer were computed by uvlt_text_encode for these
                               sequences (ids / text_mask are constant per sequence): the BERT embedding and the
                               BERT-only layers are not re-run, their rows are restored from the cache.  Bit-identical. */
@@ -179,12 +184,20 @@ UVLT_API int uvlt_track_frame_host(uvlt_handle h, const uint8_t* search_u8_host,
  * run back to back.  `state` is DEVICE fp64 [B,4] (x, y, w, h in frame pixels), updated in place.
  * out_host: HOST fp64 [B,10] = new state (4), network box cx cy w h (4), score, argmax index (-1 when the crop side
  * is < 1 pixel: the reference raises "Too small bounding box.", the state is then left unchanged).
- * Synchronises the stream before returning. */
+ * Synchronises the stream before returning (unless UVLT_NO_SYNC). */
 UVLT_API int uvlt_track_frame_image_host(uvlt_handle h, const uint8_t* frames_host, int32_t frame_h, int32_t frame_w,
                                          double* state, double search_factor, const float* tmpl, const int64_t* ids,
                                          const float* text_mask, const float* prompt, const int64_t* flag,
                                          const double* window, int32_t batch, int32_t flags, int32_t has_cont,
                                          float* max_score, float* snapshot, double* out_host, void* stream);
+
+/* cudaStreamSynchronize(stream): the wait that goes with UVLT_NO_SYNC. */
+UVLT_API int uvlt_stream_sync(void* stream);
+
+/* Waits for the most recent uvlt_track_frame_image_host step that used frame slot `slot` (0, or 1 with UVLT_FRAME_SLOT1) --
+ * its result rows are then in out_host -- WITHOUT waiting for work enqueued after it: a caller that has committed to its
+ * next frames enqueues step t+1 (other slot, other out_host) first and then waits for step t only. */
+UVLT_API int uvlt_step_wait(uvlt_handle h, int32_t slot);
 
 /* Asynchronous piecewise upload of the raw frames of the next uvlt_track_frame_image_host call (which is then given
  * frames_host == NULL): `nbytes` from `host` (pinned recommended) to byte offset `dst_offset` of the engine's

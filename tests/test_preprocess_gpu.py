@@ -134,18 +134,19 @@ def test_prefetched_frames_give_identical_tracks():
 
     pinned = [pinned_frames(s[0]) for s in seqs]  # the same clips in page-locked memory: uploaded without staging
     assert all(isinstance(f, PinnedFrame) and np.array_equal(f, g) for fs, s in zip(pinned, seqs) for f, g in zip(fs, s[0]))
-    for mode in ("plain", "prefetch", "broken_promise", "pinned_plain", "pinned_prefetch"):
+    for mode in ("plain", "prefetch", "broken_promise", "pinned_plain", "pinned_prefetch", "committed", "pinned_committed"):
         bt = BatchTracker(params, batch=B)
         bt.initialize([s[0][0] for s in seqs], infos)
         out = []
         src = pinned if mode.startswith("pinned") else [s[0] for s in seqs]
+        commit = mode.endswith("committed")  # the next step is enqueued before track() returns
         for t in range(1, n + 1):
             cur = [f[t] for f in src]
             nxt = [f[t + 1] for f in src] if t < n else None
             if mode in ("plain", "pinned_plain"):
                 res = bt.track(cur)
-            elif mode in ("prefetch", "pinned_prefetch"):
-                res = bt.track(cur, next_images=nxt)
+            elif mode in ("prefetch", "pinned_prefetch") or commit:
+                res = bt.track(cur, next_images=nxt, commit_next=commit)
             else:  # announce frame t+1 of the OTHER sequence order: the tracker must notice and stage `cur` itself
                 res = bt.track(cur, next_images=nxt[::-1] if nxt else None)
             out.append([r["target_bbox"] for r in res])
@@ -155,3 +156,28 @@ def test_prefetched_frames_give_identical_tracks():
     assert np.array_equal(tracks["plain"], tracks["broken_promise"])
     assert np.array_equal(tracks["plain"], tracks["pinned_plain"])
     assert np.array_equal(tracks["plain"], tracks["pinned_prefetch"])
+    assert np.array_equal(tracks["plain"], tracks["committed"])
+    assert np.array_equal(tracks["plain"], tracks["pinned_committed"])
+
+
+def test_committed_next_frames_must_be_honoured():
+    """track(..., commit_next=True) has already advanced the device state with the announced frames: a next call with
+    other frames must fail loudly, and initialize() must drop the pending step."""
+    z, x, B = 128, 256, 2
+    dims = ModelDims.base(z, x)
+    cfg = config.baseline_cfg("base", z, x, mode="BBOX")
+    params = config.parameters(cfg)
+    params.state_dict = synthetic_state_dict(dims, seed=0)
+    seqs = [synthetic_sequence(4, seed=80 + b) for b in range(B)]
+    infos = [{"init_bbox": s[1][0]} for s in seqs]
+    bt = BatchTracker(params, batch=B)
+    bt.initialize([s[0][0] for s in seqs], infos)
+    bt.track([s[0][1] for s in seqs], next_images=[s[0][2] for s in seqs], commit_next=True)
+    with pytest.raises(ValueError):
+        bt.track([s[0][3] for s in seqs])
+    bt.initialize([s[0][0] for s in seqs], infos)
+    a = bt.track([s[0][1] for s in seqs], next_images=[s[0][2] for s in seqs], commit_next=True)
+    bt.initialize([s[0][0] for s in seqs], infos)          # drops the committed step
+    b = bt.track([s[0][1] for s in seqs])
+    assert [r["target_bbox"] for r in a] == [r["target_bbox"] for r in b]
+    bt.engine.close()

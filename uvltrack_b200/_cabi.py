@@ -46,6 +46,7 @@ WANT_LOGITS = 1
 SKIP_TEXT = 2
 TEXT_CACHED = 4
 FRAME_SLOT1 = 8
+NO_SYNC = 16
 
 _P = c_void_p
 # name -> (restype, argtypes); must list every symbol include/uvlt.h declares (tests/test_cabi_symbols.py checks)
@@ -66,6 +67,8 @@ SIGNATURES = {
     "uvlt_track_frame_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "uvlt_track_frame_image_host": (c_int, [_P, _P, c_int32, c_int32, _P, C.c_double, _P, _P, _P, _P, _P, _P, c_int32,
                                             c_int32, c_int32, _P, _P, _P, _P]),
+    "uvlt_stream_sync": (c_int, [_P]),
+    "uvlt_step_wait": (c_int, [_P, c_int32]),
     "uvlt_op_crop_resize": (c_int, [_P, c_int32, c_int32, _P, C.c_double, c_int32, _P, _P, c_int32, _P]),
     "uvlt_op_box_update": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P]),
     "uvlt_op_anno2mask": (c_int, [_P, c_int32, _P, c_int32, _P]),

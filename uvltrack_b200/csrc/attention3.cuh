@@ -217,8 +217,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
   uint64_t* const s_free = s_full + 2;                // [2] the slot's 8 softmax warps hold S_t in registers
   uint64_t* const p_full = s_free + 2;                // [2] P_t stored (and O_t rescaled), 8 warp arrivals
   uint64_t* const pv_done = p_full + 2;               // [2] PV_t drained: P_t reusable, O_t includes the block
-  uint64_t* const stagger = pv_done + 2;              // slot 0 is half way through its very first block (8 warp arrivals)
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -240,7 +239,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
       mbar_init(&p_full[t], 8);
       mbar_init(&pv_done[t], 1);
     }
-    mbar_init(stagger, 8);
     for (int s = 0; s < AT3_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 2);
@@ -371,9 +369,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
       }
     };
     c_seek();
-    // slot 1 starts half a block behind slot 0 (only when its first item is a PAIR item: in a LONE item it has the
-    // shorter half of the key blocks anyway)
-    if (t == 1 && c_idx < geo.total && !c_it.lone) mbar_wait_trap(stagger, 0);
     issue_next_qk();
     int ord = 0;
 #pragma unroll 1
@@ -485,6 +480,25 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         const float alpha = (ref == m_run) ? 1.0f : ex2_approx(m_run - ref);  // 0 on the first block
         const float neg_ref = -ref;
         if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x20 + (k_blk & 15));  // reference known
+        if (i > 0) {
+          // P_t and O_t are free once PV_t of the previous block has drained (issued a block ago: checked here,
+          // ahead of the turn, so that the wait and the rare rescale of O overlap the other slot's exponentials)
+          mbar_wait_trap(&pv_done[t], (k_blk - 1) & 1);
+          tc_fence_after();
+          if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x30 + (k_blk & 15));  // pv_done seen
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // bring this half's 32 output columns to the new reference (rare)
+            const uint32_t tO = tmem_s(tid_now()) + 192 - hf * 32;
+#pragma unroll 1
+            for (int cc = 0; cc < 32; cc += 8) {
+              uint32_t o[8];
+              tmem_ld8(tO + cc, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+              tmem_st8(tO + cc, o);
+            }
+          }
+        }
         // The exponentials of the two slots take turns (token = named barriers EXP_TURN + slot; per-quadrant mbarrier
         // tokens measured slower, 75.8 against 70.6 us: four more polling warps per scheduler): left alone the slots
         // drift into phase, all four softmax warps of a scheduler then want the MUFU at the same time (a block's
@@ -508,26 +522,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         }
         if (p.pingpong) at3_bar_arrive(EXP_TURN + (t ^ 1), 512);
         if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x80 + (k_blk & 15));  // exponentials done, turn passed
-        // slot 1 starts half a block behind slot 0 (see the MMA issuer)
-        if (k_blk == 0 && t == 0 && lane == 0) mbar_arrive(stagger);
-        if (i > 0) {
-          // P_t and O_t are free once PV_t of the previous block has drained (the exponentials were computed meanwhile)
-          mbar_wait_trap(&pv_done[t], (k_blk - 1) & 1);
-          tc_fence_after();
-          if (warp == 0 && lane == 0) TRACE_PT(0x500 + 0x30 + (k_blk & 15));  // pv_done seen
-          if (__any_sync(0xffffffffu, alpha != 1.0f)) {  // bring this half's 32 output columns to the new reference (rare)
-            const uint32_t tO = tmem_s(tid_now()) + 192 - hf * 32;
-#pragma unroll 1
-            for (int cc = 0; cc < 32; cc += 8) {
-              uint32_t o[8];
-              tmem_ld8(tO + cc, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int q = 0; q < 8; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
-              tmem_st8(tO + cc, o);
-            }
-          }
-        }
         float l_blk = 0.0f;
         if (nchunk > 0) {
           l_blk += VAR >= 2 ? at3_chunk_sum_pack_x2(v[0], pk) : at2_chunk_sum_pack(v[0], pk);

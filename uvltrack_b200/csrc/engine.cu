@@ -131,6 +131,7 @@ struct uvlt_engine {
   cudaStream_t side = nullptr;
   cudaStream_t cap = nullptr;  // graphs are captured here (the caller's stream may be the legacy default stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t step_done[2] = {nullptr, nullptr};  // recorded after the result rows of a uvlt_track_frame_image_host step (per frame slot)
   std::map<int, std::unique_ptr<Plan>> plans;  // key = B * 2 + skip_text
   int last_B = 0;
   int last_cont_cols = 3;
@@ -952,7 +953,9 @@ int uvlt_create(const uvlt_config* cfg, uvlt_handle* out) {
       cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->step_done[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->step_done[1], cudaEventDisableTiming) != cudaSuccess) {
     if (!*get_error()) set_error("uvlt_create: CUDA resource creation failed");
     uvlt_destroy(e);
     return 1;
@@ -974,6 +977,8 @@ void uvlt_destroy(uvlt_handle e) {
   if (e->cap) cudaStreamDestroy(e->cap);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  for (auto& ev : e->step_done)
+    if (ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -1223,7 +1228,19 @@ int uvlt_track_frame_image_host(uvlt_handle e, const uint8_t* frames_host, int32
   e->last_cont_cols = e->cfg.softmax_one ? 3 : 2;
   if (track_decode(e, s, B, window, has_cont, max_score, snapshot, e->track_out, state, frame_h, frame_w)) return 1;
   ENG_CUDA(cudaMemcpyAsync(out_host, e->out10_d, static_cast<size_t>(B) * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  ENG_CUDA(cudaStreamSynchronize(s));
+  ENG_CUDA(cudaEventRecord(e->step_done[slot], s));
+  if (!(flags & UVLT_NO_SYNC)) ENG_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int uvlt_stream_sync(void* stream) {
+  ENG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int uvlt_step_wait(uvlt_handle e, int32_t slot) {
+  if (!e || slot < 0 || slot > 1) { set_error("uvlt_step_wait: bad argument"); return 1; }
+  ENG_CUDA(cudaEventSynchronize(e->step_done[slot]));
   return 0;
 }
 

@@ -230,7 +230,9 @@ class BatchTracker:
         self.out = torch.zeros(self.B, 6, dtype=torch.float32, pin_memory=True)
         self.out_np = self.out.numpy()
         self.state_dev = torch.zeros(self.B, 4, dtype=torch.float64, device=dev)
-        self.out10 = torch.zeros(self.B, 10, dtype=torch.float64, pin_memory=True)
+        # result rows of a device-resident step, one buffer per frame slot: a step committed ahead (commit_next) writes its
+        # rows while the host may still be reading the previous step's
+        self.out10 = torch.zeros(2, self.B, 10, dtype=torch.float64, pin_memory=True)
         self.out10_np = self.out10.numpy()
         self.frames = None  # pinned uint8 [B, H, W, 3], allocated for the first frame size seen
         self._fast = None   # raw pointers of the per-frame engine call, bound per frame size
@@ -238,13 +240,14 @@ class BatchTracker:
         # double buffering of the frame upload (track(..., next_images=...)): pinned staging per slot, copy stream, events
         self._pf_frames, self._pf_np = [None, None], [None, None]
         self._pf_stream, self._pf_events, self._pf_pending = None, None, None
+        self._ahead = None  # (frames, staging slot) of a step enqueued ahead by track(..., commit_next=True)
         self.h2d_bytes = 0  # bytes of raw frames uploaded by track() so far (search windows only)
         # host wall-clock seconds spent per phase of track() so far (bench.py reports them as e2e_phases):
         #   stage_h2d  pageable frame -> pinned staging copies + enqueueing the async window uploads
         #   engine     the blocking engine call: H2D completion, crop/resize, forward, merge, box update, D2H, sync
         #   host_post  per-sequence bookkeeping of the result rows
         #   prompt     prompt updates (every UPDATE_INTERVAL frames)
-        self.phase_s = {"stage_h2d": 0.0, "engine": 0.0, "host_post": 0.0, "prompt": 0.0}
+        self.phase_s = {"stage_h2d": 0.0, "engine": 0.0, "host_post": 0.0, "prompt": 0.0, "launch_ahead": 0.0}
         self.skip_text = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -321,6 +324,9 @@ class BatchTracker:
         """lib/test/tracker/uvltrack.py:70-104 for every sequence of the batch."""
         import torch
 
+        if self._ahead is not None:  # a step committed by the previous sequence's last track() call: let it drain, drop it
+            torch.cuda.synchronize()
+            self._ahead = None
         d, mode = self.dims, self.cfg.TEST.MODE
         ids_all = np.zeros((self.B, d.text_len), dtype=np.int64)
         mask_all = np.zeros((self.B, d.text_len), dtype=np.float32)
@@ -418,7 +424,7 @@ class BatchTracker:
             "state": self.state_dev.data_ptr(), "template": self.template.data_ptr(), "ids": self.ids.data_ptr(),
             "text_mask": self.text_mask.data_ptr(), "prompt": self.prompt.data_ptr(), "flag": self.flag.data_ptr(),
             "window": self.window_dev.data_ptr(), "max_score": self.max_score_dev.data_ptr(),
-            "snapshot": self.snapshot.data_ptr(), "out10": self.out10.data_ptr(),
+            "snapshot": self.snapshot.data_ptr(), "out10": [self.out10[0].data_ptr(), self.out10[1].data_ptr()],
         }
 
     def _prefetch_job(self, images, slot, H, W, b0, b1):
@@ -438,6 +444,35 @@ class BatchTracker:
                 raise RuntimeError("uvlt_upload_frames_slot failed")
         return (b1 - b0) * per
 
+    def _enqueue_step(self, H, W, slot, stream):
+        """One tracker step (device crop of frame-staging slot ``slot``, forward, merge, box update, result rows to the
+        pinned ``out10``) enqueued on ``stream`` WITHOUT synchronising (UVLT_NO_SYNC)."""
+        from . import _cabi
+
+        f = self._fast
+        rc = self.engine.lib.uvlt_track_frame_image_host(
+            self.engine.h, None, H, W, f["state"], float(self.params.search_factor), f["template"], f["ids"], f["text_mask"],
+            f["prompt"], f["flag"], f["window"], self.B,
+            (_cabi.SKIP_TEXT if self.skip_text else 0) | (_cabi.TEXT_CACHED if self.text_cached else 0) |
+            (_cabi.FRAME_SLOT1 if slot else 0) | _cabi.NO_SYNC,
+            int(self.has_cont), f["max_score"], f["snapshot"], f["out10"][slot], stream)
+        if rc:
+            _cabi.check(rc, "uvlt_track_frame_image_host")
+
+    def _launch_ahead(self):
+        """commit_next: enqueue the next step now.  Its frames were prefetched into the other staging slot by this call;
+        the compute stream waits for those copies, nothing on the host does."""
+        import torch
+
+        futs, pf_images, pf_slot, (H, W) = self._pf_pending
+        self._pf_pending = None
+        nbytes = sum(f_.result() for f_ in futs)
+        self._pf_events[pf_slot].record(self._pf_stream)
+        torch.cuda.current_stream().wait_event(self._pf_events[pf_slot])
+        self.h2d_bytes += nbytes
+        self._enqueue_step(H, W, pf_slot, torch.cuda.current_stream().cuda_stream)
+        self._ahead = (pf_images, pf_slot)
+
     def _prefetch_pinned(self, images, slot, per):
         """Double buffering without staging: the next step's frames are page-locked already (PinnedFrame), so the worker
         thread only enqueues B asynchronous copies on the copy stream; no host thread reads a pixel."""
@@ -449,8 +484,14 @@ class BatchTracker:
                 raise RuntimeError("uvlt_upload_frames_slot failed")
         return total
 
-    def track(self, images, raise_on_failure: bool = True, next_images=None):
+    def track(self, images, raise_on_failure: bool = True, next_images=None, commit_next: bool = False):
         """lib/test/tracker/uvltrack.py:106-140 for every sequence of the batch.
+
+        ``commit_next`` (with ``next_images``): the caller GUARANTEES that its next call passes exactly ``next_images``.
+        The next step is then enqueued on the device before this call returns -- as soon as this step's rows are read and
+        a due prompt update is applied -- so the GPU does not idle while the host builds this step's results and the
+        caller gets around to its next call (at batch 1 that gap was ~50 us of a 0.72 ms step).  A next call with
+        other frames raises ``ValueError`` (the device state has already advanced); ``initialize`` drops a pending step.
 
         ``next_images`` (optional, same frame size): the frames the NEXT call will be given.  They are staged and uploaded
         into the engine's second frame buffer by a worker thread while this call's forward runs, so the next call starts
@@ -494,11 +535,17 @@ class BatchTracker:
                 dev = torch.cuda.current_device()
                 self._pool = ThreadPoolExecutor(max_workers=min(8, max(2, self.B)),
                                                 initializer=lambda: torch.cuda.set_device(dev))
+            ahead = self._ahead
+            self._ahead = None
+            if ahead is not None and not (len(ahead[0]) == len(images) and all(a is b_ for a, b_ in zip(ahead[0], images))):
+                lib.uvlt_stream_sync(stream)
+                raise ValueError("track(): these are not the frames committed with commit_next in the previous call")
             # were these very frames prefetched by the previous call?
-            pf = self._pf_pending
-            self._pf_pending = None
-            use_slot = 0
-            prefetched = False
+            pf = self._pf_pending if ahead is None else None
+            if ahead is None:
+                self._pf_pending = None
+            use_slot = ahead[1] if ahead is not None else 0
+            prefetched = ahead is not None
             if pf is not None:
                 futs, pf_images, pf_slot, pf_hw = pf
                 nbytes = sum(f_.result() for f_ in futs)  # staging + enqueue finished (normally long ago: under the last forward)
@@ -557,20 +604,27 @@ class BatchTracker:
                     cuts = [self.B * k // njobs for k in range(njobs + 1)]
                     self._pf_pending = ([self._pool.submit(self._prefetch_job, nxt, nslot, H, W, cuts[k], cuts[k + 1])
                                          for k in range(njobs)], nxt, nslot, (H, W))
+            if ahead is None:
+                self._enqueue_step(H, W, use_slot, stream)
+            # commit_next: the next step goes into the stream BEHIND this one before the host waits for this one, unless
+            # this frame may update the prompt (every update_interval-th frame: the update must come first; the next
+            # step is then enqueued after it, below)
+            may_update = self.has_cont and self.frame_id % self.update_interval == 0
+            if commit_next and self._pf_pending is not None and not may_update and not any(self.failed):
+                t_la = time.perf_counter()
+                self._launch_ahead()
+                self.phase_s["launch_ahead"] += time.perf_counter() - t_la
+                t_start += time.perf_counter() - t_la  # keep it out of stage_h2d
             t_staged = time.perf_counter()
-            rc = lib.uvlt_track_frame_image_host(h, None, H, W, f["state"], float(self.params.search_factor), f["template"],
-                                                 f["ids"], f["text_mask"], f["prompt"], f["flag"], f["window"], self.B,
-                                                 (2 if self.skip_text else 0) | (4 if self.text_cached else 0) |
-                                                 (8 if use_slot else 0),
-                                                 int(self.has_cont), f["max_score"], f["snapshot"], f["out10"], stream)
+            rc = lib.uvlt_step_wait(h, use_slot)
             t_engine = time.perf_counter()
             if rc:
                 from . import _cabi
 
-                _cabi.check(rc, "uvlt_track_frame_image_host")
+                _cabi.check(rc, "uvlt_step_wait")
             rows = []
             for b in range(self.B):
-                row = self.out10_np[b]
+                row = self.out10_np[use_slot, b]
                 if row[9] < 0:  # crop side < 1 px: the device left this sequence's state untouched
                     if raise_on_failure:
                         raise Exception("Too small bounding box.")  # lib/train/data/processing_utils.py:180
@@ -630,6 +684,10 @@ class BatchTracker:
             for b in update:
                 self.max_score[b] = 0.0
         t_end = time.perf_counter()
+        if commit_next and self._pf_pending is not None and self._ahead is None and t_staged is not None \
+                and not any(self.failed):
+            self._launch_ahead()
+            self.phase_s["launch_ahead"] += time.perf_counter() - t_end
         ph = self.phase_s
         if t_staged is not None:
             ph["stage_h2d"] += t_staged - t_start
