@@ -75,14 +75,19 @@ class _FakeBatchTracker:
 
     def __init__(self, params, batch=1):
         self.B, self.state, self.failed, self.n, self.names = batch, None, None, 0, None
+        self.committed = None  # frames promised with commit_next: the next call must pass these very objects
 
     def initialize(self, images, infos):
         self.state = [list(i["init_bbox"]) for i in infos]
         self.names = [i["seq_name"] for i in infos]
         self.failed = [None] * self.B
         self.n = 0
+        self.committed = None
 
-    def track(self, images, raise_on_failure=True, next_images=None):
+    def track(self, images, raise_on_failure=True, next_images=None, commit_next=False):
+        if self.committed is not None:  # the contract of BatchTracker.track(commit_next=True)
+            assert len(images) == len(self.committed) and all(a is b for a, b in zip(images, self.committed))
+        self.committed = list(next_images) if (commit_next and next_images is not None) else None
         self.n += 1
         out = []
         for b in range(self.B):

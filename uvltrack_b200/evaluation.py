@@ -188,9 +188,13 @@ def run_dataset_batched(dataset: Seq[Sequence], tracker: Tracker, batch: int, ra
             cached = next_cache[0][1] if next_cache[0] is not None and next_cache[0][0] == t else None
             for b, s in enumerate(seqs):
                 try:
-                    if dead[b] is None:
-                        # reuse the very array objects handed to the tracker as `next_images` (it recognises them)
-                        last[b] = cached[b] if cached is not None else read_image(s.frames[min(t, len(s) - 1)])
+                    if cached is not None:
+                        # the very array objects handed to the tracker as `next_images` (it recognises them) -- for every
+                        # lane, also one that failed in the step before: the step was committed with these frames, and
+                        # what a frozen lane is shown does not matter
+                        last[b] = cached[b]
+                    elif dead[b] is None:
+                        last[b] = read_image(s.frames[min(t, len(s) - 1)])
                 except Exception as e:  # an unreadable frame ends this sequence only
                     dead[b] = f"{type(e).__name__}: {e}"
                 if last[b] is None:
@@ -204,7 +208,8 @@ def run_dataset_batched(dataset: Seq[Sequence], tracker: Tracker, batch: int, ra
                     next_cache[0] = (t + 1, nxt)
                 except Exception:
                     nxt = None
-            res = bt.track(frames, raise_on_failure=False, next_images=nxt)
+            # ... and commit to them: step t+1 is enqueued behind step t before the host waits for step t
+            res = bt.track(frames, raise_on_failure=False, next_images=nxt, commit_next=nxt is not None)
             dt = (time.time() - t0) / len(group)
             for b, s in enumerate(group):
                 if dead[b] is None and res[b].get("failed"):
