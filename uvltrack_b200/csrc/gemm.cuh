@@ -131,6 +131,35 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias
     if (ep.in_rows_per_b > 0) { seq_q0 = r_first / ep.in_rows_per_b; seq_rem0 = r_first - seq_q0 * ep.in_rows_per_b; }
     if (ep.resid_period > 0) per_rem0 = r_first % ep.resid_period;
   }
+  // fp32 flavour: the residual rows of this tile do not depend on the accumulator -- fetch (up to eight row groups of) them
+  // BEFORE waiting for it.  ncu on the CTA-pair out-proj GEMM (M = 17696, K = 768): 53 % of all warp stalls were the
+  // long-scoreboard wait on exactly these loads, issued four at a time after the accumulator had landed
+  // (profiles/r02_b32_gemm_full.md); the kernel ran at 632 TFLOP/s with DRAM at 26 % and the tensor pipe at 32 %.
+  constexpr int NPRE = (F32 && NPASS == 1 && ITERS <= 8) ? ITERS : 0;  // 32-column passes (wider ones would spill)
+  float4 rpre[NPRE > 0 ? NPRE : 1];
+  if (NPRE > 0) {
+    int q = seq_q0, rem = seq_rem0, per = per_rem0;
+    const int rows_left = shape.M - r_first;
+#pragma unroll
+    for (int it = 0; it < NPRE; ++it) {
+      long long rr;
+      if (ep.in_rows_per_b > 0) {
+        if (rem >= ep.in_rows_per_b) { rem -= ep.in_rows_per_b; ++q; }
+        rr = static_cast<long long>(q) * ep.out_rows_per_b + ep.out_row_off + rem;
+      } else {
+        rr = rem;
+      }
+      rem += RPI;
+      if (ep.resid_period > 0) {
+        if (per >= ep.resid_period) per -= ep.resid_period;
+        rr = per;
+        per += RPI;
+      }
+      rpre[it] = (ep.resid && it * RPI < rows_left && sp == 0)
+                     ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col0)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   mbar_wait(acc_bar, acc_parity);
   tc_fence_after();
   if (threadIdx.x == 64) TRACE_PT(0x105);
@@ -194,7 +223,8 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias
     const int rows_left = shape.M - r_first;
     const uint32_t src = stage_w + (lane / CPR) * ROWB;
     constexpr int UN = ITERS < 4 ? ITERS : 4;
-#pragma unroll 1
+    // fully unrolled when residual rows were prefetched (rpre must be indexed statically to stay in registers)
+#pragma unroll(NPRE > 0 ? 16 : 1)
     for (int it0 = 0; it0 < ITERS; it0 += UN) {
       float4 v[UN];
 #pragma unroll
@@ -221,8 +251,11 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, const float* s_bias
             rr = per_rem;
             per_rem += RPI;
           }
-          r4[u] = (ep.resid && ok && sp == 0) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NPRE > 0 && it0 + u < NPRE)
+            r4[u] = rpre[it0 + u];
+          else
+            r4[u] = (ep.resid && ok && sp == 0) ? *reinterpret_cast<const float4*>(ep.resid + rr * ep.resid_ld + col)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
