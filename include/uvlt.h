@@ -238,6 +238,13 @@ UVLT_API int uvlt_op_box_update(const float* net_boxes, const double* resize_fac
  * mask uint8 [B, size*size] (1 = cell centre inside the box, plus the cell under the box centre).  Device pointers. */
 UVLT_API int uvlt_op_anno2mask(const float* boxes, int32_t size, uint8_t* mask, int32_t batch, void* stream);
 
+/* grounding_resize (lib/train/data/processing_utils.py:60-141, image part; NL-mode first frame, lib/test/tracker/
+ * uvltrack.py:45-62): frames uint8 [B, frame_h, frame_w, 3] -> out uint8 [B, out_size, out_size, 3]: the whole frame
+ * resized with its aspect ratio kept (longer side = out_size, cv2.resize INTER_LINEAR 8-bit arithmetic, bit-exact) and
+ * centred in a canvas of zeros.  Device pointers. */
+UVLT_API int uvlt_op_grounding_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, int32_t out_size,
+                                      uint8_t* out, int32_t batch, void* stream);
+
 /* Preprocessor_wo_mask.process (lib/test/tracker/tracker_utils.py:25-29): crops uint8 [B,S,S,3] -> out fp32 [B,3,S,S],
  * ((x / 255) - mean) / std.  Device pointers.  (Search crops never take this path: their normalisation is fused into the
  * patch embedding; this is for the template / context crops of Tracker.initialize.) */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "uvlt_op_box_update": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P]),
     "uvlt_op_anno2mask": (c_int, [_P, c_int32, _P, c_int32, _P]),
     "uvlt_op_normalize_u8": (c_int, [_P, _P, c_int32, c_int32, _P]),
+    "uvlt_op_grounding_resize": (c_int, [_P, c_int32, c_int32, c_int32, _P, c_int32, _P]),
     "uvlt_text_encode": (c_int, [_P, _P, _P, _P, c_int32, _P]),
     "uvlt_upload_frames": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P]),
     "uvlt_upload_frames_slot": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int32, _P]),

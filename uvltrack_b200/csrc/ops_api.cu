@@ -157,6 +157,19 @@ int uvlt_op_anno2mask(const float* boxes, int32_t size, uint8_t* mask, int32_t B
   return 0;
 }
 
+int uvlt_op_grounding_resize(const uint8_t* frames, int32_t frame_h, int32_t frame_w, int32_t out_size, uint8_t* out,
+                             int32_t B, void* stream) {
+  if (!frames || !out || B < 1 || frame_h < 2 || frame_w < 2 || out_size < 1 || out_size > 4096) {
+    set_error("uvlt_op_grounding_resize: bad argument");
+    return 1;
+  }
+  GroundParams gp{frames, frame_h, frame_w, out_size, out};
+  UVLT_LAUNCH(grounding_resize_kernel, dim3((out_size * out_size + 255) / 256, B), dim3(256), 0,
+              static_cast<cudaStream_t>(stream), gp);
+  if (cudaGetLastError() != cudaSuccess) { set_error("grounding_resize launch failed"); return 1; }
+  return 0;
+}
+
 int uvlt_op_normalize_u8(const uint8_t* crops, float* out, int32_t size, int32_t B, void* stream) {
   if (!crops || !out || B < 1 || size < 1) { set_error("uvlt_op_normalize_u8: bad argument"); return 1; }
   UVLT_LAUNCH(normalize_u8_kernel, dim3((size * size + 255) / 256, B), dim3(256), 0, static_cast<cudaStream_t>(stream),

@@ -158,6 +158,59 @@ static __global__ void anno2mask_kernel(const float* boxes, int size, uint8_t* m
 
 // Preprocessor_wo_mask.process (lib/test/tracker/tracker_utils.py:25-29): uint8 HWC crop -> fp32 [3, S, S],
 // ((x / 255) - mean) / std in fp32 in that order.
+// grounding_resize (lib/train/data/processing_utils.py:60-141, image part): the WHOLE frame resized without changing its
+// aspect ratio so that its longer side is out_sz (cv2.resize INTER_LINEAR, the same 8-bit fixed-point arithmetic as
+// crop_resize_kernel, but with separate x / y scales and no border: every tap lies inside the frame), centred in an
+// out_sz x out_sz canvas of zeros.  NL-mode first frame of Tracker.initialize (lib/test/tracker/uvltrack.py:45-62).
+struct GroundParams {
+  const uint8_t* frames;   // [B, H, W, 3] RGB
+  int H, W;
+  int out_sz;
+  uint8_t* out;            // [B, out_sz, out_sz, 3]
+};
+
+static __global__ void __launch_bounds__(256) grounding_resize_kernel(const GroundParams p) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= p.out_sz * p.out_sz) return;
+  const int dy = pix / p.out_sz, dx = pix - dy * p.out_sz;
+  // processing_utils.py:83-100 (Python: int(output_sz * h / w) = truncation of a double quotient; pads int((sz - o) / 2),
+  // the first one a pixel larger when the difference is odd)
+  int ow, oh;
+  if (p.W > p.H) {
+    ow = p.out_sz;
+    oh = static_cast<int>(static_cast<double>(p.out_sz * p.H) / static_cast<double>(p.W));
+  } else {
+    oh = p.out_sz;
+    ow = static_cast<int>(static_cast<double>(p.out_sz * p.W) / static_cast<double>(p.H));
+  }
+  int y1 = (p.out_sz - oh) / 2, x1 = (p.out_sz - ow) / 2;
+  if (2 * y1 + oh != p.out_sz) y1 += 1;
+  if (2 * x1 + ow != p.out_sz) x1 += 1;
+  uint8_t* dst = p.out + (static_cast<long long>(b) * p.out_sz * p.out_sz + pix) * 3;
+  const int ry = dy - y1, rx = dx - x1;
+  if (ry < 0 || ry >= oh || rx < 0 || rx >= ow || ow < 1 || oh < 1) { dst[0] = dst[1] = dst[2] = 0; return; }
+  const double scale_x = 1.0 / (static_cast<double>(ow) / static_cast<double>(p.W));
+  const double scale_y = 1.0 / (static_cast<double>(oh) / static_cast<double>(p.H));
+  int sx, ax0, ax1, sy, by0, by1;
+  linear_tap(rx, scale_x, p.W, true, &sx, &ax0, &ax1);
+  linear_tap(ry, scale_y, p.H, false, &sy, &by0, &by1);
+  const int sx1 = min(sx + 1, p.W - 1);
+  const int ry0 = min(max(sy, 0), p.H - 1), ry1 = min(max(sy + 1, 0), p.H - 1);
+  const uint8_t* img = p.frames + static_cast<long long>(b) * p.H * p.W * 3;
+  const uint8_t* row0 = img + static_cast<long long>(ry0) * p.W * 3;
+  const uint8_t* row1 = img + static_cast<long long>(ry1) * p.W * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int r0 = row0[sx * 3 + c] * ax0 + row0[sx1 * 3 + c] * ax1;
+    const int r1 = row1[sx * 3 + c] * ax0 + row1[sx1 * 3 + c] * ax1;
+    const int v = (((by0 * (r0 >> 4)) >> 16) + ((by1 * (r1 >> 4)) >> 16) + 2) >> 2;  // VResizeLinear<uchar>
+    dst[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+  }
+}
+
 static __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* crops, float* out, int S, int B) {
   pdl_wait();
   pdl_trigger();

@@ -277,7 +277,20 @@ class BatchTracker:
 
         d = self.dims
         h, w = image.shape[:2]
-        ground = torch.from_numpy(pp.normalize_image(pp.grounding_resize(image, self.params.grounding_size))).cuda()
+        if self.device_preprocess and image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3:
+            # whole-frame resize + padding + normalisation on the device (bit-exact with the cv2 path below)
+            from . import _cabi
+
+            lib, S = self.engine.lib, int(self.params.grounding_size)
+            frame = torch.from_numpy(np.ascontiguousarray(image)).cuda()
+            canvas = torch.empty(1, S, S, 3, dtype=torch.uint8, device="cuda")
+            ground = torch.empty(1, 3, S, S, dtype=torch.float32, device="cuda")
+            stream = _cabi.current_stream()
+            _cabi.check(lib.uvlt_op_grounding_resize(frame.data_ptr(), h, w, S, canvas.data_ptr(), 1, stream),
+                        "uvlt_op_grounding_resize")
+            _cabi.check(lib.uvlt_op_normalize_u8(canvas.data_ptr(), ground.data_ptr(), S, 1, stream), "uvlt_op_normalize_u8")
+        else:
+            ground = torch.from_numpy(pp.normalize_image(pp.grounding_resize(image, self.params.grounding_size))).cuda()
         template = torch.zeros(1, 3, d.template_size, d.template_size, device="cuda")
         tm = torch.zeros(1, d.nz, dtype=torch.uint8, device="cuda")
         cm = torch.zeros(1, d.nx, dtype=torch.uint8, device="cuda")
