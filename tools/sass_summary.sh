@@ -25,6 +25,9 @@ cuobjdump -sass $LIB | awk '
     echo "$line" | sed "s|\`$sym\`|\`$dem\`|"
   done | sort -u
 echo
+echo "The one BRA.U.ANY of the attention3 kernels wraps the UTMASTG (TMA bulk store of an output tile) that the slot's store"
+echo "thread issues once per work item, outside the key-block loop (attention3.cuh, item epilogue)."
+echo
 echo "PTX (\`cuobjdump -ptx\` is empty: the library ships SASS for sm_100a only); source-level instructions:"
 echo
 echo '```'
