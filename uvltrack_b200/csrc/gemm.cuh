@@ -653,9 +653,13 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
           gemm_epilogue<CW, EPI>(stage, bias + c, &acc_full[buf], par, tmem_acc + c, m0, nh + c, g, 0, shape, ep, warp,
                                  lane TRACE_ARGS);
       }
-      // this warp's TMEM reads of the tile are complete (the epilogue ends its stage 1 with a tcgen05 fence)
+      // this warp's TMEM reads of the tile are complete (the epilogue ends its stage 1 with a tcgen05 fence, which is what
+      // orders them before the leader's next MMAs into this buffer).  RELAXED arrive: with .release the fp32 flavour
+      // waited here for its global stores of the tile to be performed cluster-wide (MEMBAR.ALL.CTA + ERRBAR: 12 % of
+      // the out-proj kernel's stall samples, profiles/r02_b32_gemm_full.md) although nobody consumes them through this
+      // barrier.
       if (lane == 0)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty + buf * 8) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty + buf * 8) : "memory");
       if (TMA_ST) {
         fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the TMA (async proxy)
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
