@@ -477,7 +477,12 @@ constexpr int GEMM2_STAGE_BYTES = GEMM_BM * GEMM_BK * 2 + (GEMM2_BN / 2) * GEMM_
 constexpr int GEMM2_GROUP_COLS = GEMM2_BN / GEMM2_EPI_GROUPS;
 constexpr int GEMM2_EPI_BYTES = GEMM2_EPI_GROUPS * GEMM_BM * GEMM2_GROUP_COLS * 2;
 constexpr int GEMM2_MAX_STAGES = 5;
-constexpr int gemm2_smem_bytes(int stages) { return stages * GEMM2_STAGE_BYTES + GEMM2_EPI_BYTES + 256 + 128 * 4; }
+// ring + staging tiles + barriers + a zero bias row + per epilogue group two 64-float bias rows (double-buffered by tile)
+constexpr int GEMM2_BIAS_BYTES = GEMM2_EPI_GROUPS * 2 * GEMM2_GROUP_COLS * 4;
+constexpr int gemm2_smem_bytes(int stages) {
+  return stages * GEMM2_STAGE_BYTES + GEMM2_EPI_BYTES + 256 + 128 * 4 + GEMM2_BIAS_BYTES;
+}
+static_assert(gemm2_smem_bytes(GEMM2_MAX_STAGES) <= 227 * 1024, "CTA-pair GEMM: shared memory budget");
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
@@ -496,7 +501,8 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
   uint64_t* acc_full = empty_bar + GEMM2_MAX_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_zero = reinterpret_cast<float*>(stage_base + GEMM2_EPI_BYTES + 256);  // bias of a bias-less GEMM
+  float* s_zero = reinterpret_cast<float*>(stage_base + GEMM2_EPI_BYTES + 256);  // bias of a bias-less GEMM (unused)
+  float* s_bias2 = s_zero + 128;  // [groups][2][64]: the current / next tile's bias slice of each epilogue group
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -640,7 +646,15 @@ gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_
       const uint32_t par = (it >> 1) & 1;
       const uint32_t tmem_acc = tmem_base + buf * BN + half * GC;
       const int nh = n0 + half * GC;
-      const float* bias = ep.bias ? ep.bias + g * ep.bias_gstride + nh : s_zero;
+      // The tile's 64 bias values go to shared memory before the accumulator is waited for: read from global memory in
+      // stage 1 (this kernel leaves ~3 KB of L1) every FADD of the bias was a long-scoreboard stall, ~15 % of the qkv
+      // kernel's stall samples (profiles/r02_b32_gemm_full.md).  Double-buffered by tile: a warp of the group may still
+      // be in stage 1 of the previous tile.
+      float* const sb = s_bias2 + (half * 2 + buf) * GC;
+      const int tg = threadIdx.x - 64 - half * 128;  // thread index inside the epilogue group
+      if (tg < GC) sb[tg] = ep.bias ? __ldg(ep.bias + g * ep.bias_gstride + nh + tg) : 0.0f;
+      const float* bias = sb;
+      if (!TMA_ST) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (TMA_ST) {
         if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free again
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
