@@ -297,15 +297,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     // which key blocks carry a non-zero bias (warp-uniform bit mask); all other full blocks take the fast path
     uint32_t biased = 0;
     if (p.bias) {
+      // lane-strided over the whole sequence with NO vote inside the loop: the loads are independent and pipeline.  (One
+      // __any_sync per block made this a chain of dependent L2 round trips -- 24 % of the stall samples of the batch-1
+      // kernel, profiles/r02_b1_attn_full.md.)
       const float* bb = p.bias + static_cast<long long>(b) * p.n;
-      for (int j = 0; j < nblk; ++j) {
-        bool nz = false;
-        for (int i = lane; i < ATT_BKV; i += 32) {
-          const int k = j * ATT_BKV + i;
-          nz |= (k < p.n) && (__ldg(bb + k) != 0.0f);
-        }
-        if (__any_sync(0xffffffffu, nz)) biased |= 1u << j;
-      }
+#pragma unroll 4
+      for (int k = lane; k < p.n; k += 32)
+        if (__ldg(bb + k) != 0.0f) biased |= 1u << (k / ATT_BKV);
+      biased = __reduce_or_sync(0xffffffffu, biased);
     }
     float m_run = -INFINITY;  // reference of the running sum / output (scaled log2 domain): the largest score seen,
                               // moved only when the maximum grows by more than 2^8 (P stays <= 256; exact after O / l)

@@ -441,15 +441,15 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         const int hv16 = min(64, max(0, ((kv_valid + 15) & ~15) - hf * 64));  // columns of this half the PV MMA may read
         const int nchunk = (hv16 + 31) >> 5;
         const int lim0 = kv_valid - hf * 64;  // real keys in chunk 0 of this half (chunk 1: lim0 - 32); may be <= 0 or >= 32
-        // key bias of this half's two chunks (lane = key), fetched before the wait; chunk-uniform path selection
+        // key bias of this half's two chunks (lane = key): the loads are ISSUED here, ahead of the wait for S, and first
+        // USED after the scores are in registers (used right away -- the first version scaled them here -- every block paid
+        // the L2 round trip: 5 % of the kernel's stall samples inside the engine, profiles/r02_b32_attn_full.md)
         float bv0 = 0.0f, bv1 = 0.0f;
         if (bb) {
           const int k0 = (jb + i) * AT3_BK + hf * 64 + lane;
-          if (k0 < p.n) bv0 = __ldg(bb + k0) * ATT_LOG2E;
-          if (k0 + 32 < p.n) bv1 = __ldg(bb + k0 + 32) * ATT_LOG2E;
+          if (k0 < p.n) bv0 = __ldg(bb + k0);
+          if (k0 + 32 < p.n) bv1 = __ldg(bb + k0 + 32);
         }
-        const bool gen0 = __any_sync(0xffffffffu, bv0 != 0.0f) || lim0 < 32;
-        const bool gen1 = __any_sync(0xffffffffu, bv1 != 0.0f) || lim0 < 64;
         const float scale = p.scale_log2;
         uint32_t v[2][32], pk[16];
         mbar_wait_trap(&s_full[t], k_blk & 1);
@@ -462,6 +462,10 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);  // QK of the slot's next block may overwrite S
+        bv0 *= ATT_LOG2E;
+        bv1 *= ATT_LOG2E;
+        const bool gen0 = __any_sync(0xffffffffu, bv0 != 0.0f) || lim0 < 32;  // chunk-uniform path selection
+        const bool gen1 = __any_sync(0xffffffffu, bv1 != 0.0f) || lim0 < 64;
         // ---- block maximum: own half, then the row's other half through shared memory ----
         float m_half = -INFINITY;
         if (nchunk > 0) m_half = gen0 ? at3_chunk_max_m(v[0], scale, bv0, lim0) : at2_chunk_max<0>(v[0], scale, 0, 32) * scale;
