@@ -456,8 +456,11 @@ Plan* get_plan(uvlt_engine* e, int B, bool skip_text, bool exact_stream = false,
     if (gemm_prepare(&lp.fc2, e->hid, Hd, 0, w.fc2_w, Hd, 0, M, D, Hd, 1, sk > 1 ? 64 : e->force_bn,
                      ep_stream(e, w.fc2_b, rows, 0), sk))
       return nullptr;
-    if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : e->bias_vis, e->att, nullptr, 0,
-                     e->Bm))
+    // UVLT_SKIP_TEXT is the caller's statement that every flag of the batch is 0 (BBOX): no image key is masked then
+    // (cat_mask, modality_unified_feature_extractor.py:43-50), the image bias is all zeros, and a zero bias gives
+    // bit-identical probabilities to no bias at all -- so the kernel is not even asked to look at it
+    if (attn_prepare(&p->vit_attn[i], e->qkv, B, rows, e->H, joint ? e->bias_joint : (skip_text ? nullptr : e->bias_vis),
+                     e->att, nullptr, 0, e->Bm))
       return nullptr;
   }
   if (!skip_text) {
