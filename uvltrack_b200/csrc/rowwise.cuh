@@ -34,7 +34,13 @@ struct LnParams {
   long long partial_stride;
 };
 
-template <int NV>  // D = NV * 128  (768 -> 6, 1024 -> 8)
+constexpr int LN_MAX_PARTIALS = 5;  // fc2 is cut at most six ways (pick_splits)
+
+// PART: the rows carry split-K partials of the preceding fc2.  Their loads are all issued BEFORE the first add (one L2
+// round trip instead of one per partial: the batch-1 LayerNorm after a six-way fc2 took 6.5 us against 4.0 us without
+// partials, profiles/r02_b1_launches.md); the adds keep the fixed order s = 0 .. n-1.  A separate instantiation, so that
+// the large-batch LayerNorm (no partials, HBM bound) keeps its registers and occupancy.
+template <int NV, bool PART>  // D = NV * 128  (768 -> 6, 1024 -> 8)
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   pdl_wait();
   pdl_trigger();
@@ -48,12 +54,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   float4 x[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) x[k] = *reinterpret_cast<const float4*>(src + k * 128 + lane * 4);
-  for (int sp = 0; sp < (i < p.partial_rows ? p.n_partials : 0); ++sp) {
-    const float* ps = p.partials + sp * p.partial_stride + (src - p.x);
+  if (PART) {
+    const int np = i < p.partial_rows ? p.n_partials : 0;  // <= LN_MAX_PARTIALS (checked on the host)
+    float4 pv[LN_MAX_PARTIALS][NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(ps + k * 128 + lane * 4);
-      x[k].x += a.x; x[k].y += a.y; x[k].z += a.z; x[k].w += a.w;
+    for (int sp = 0; sp < LN_MAX_PARTIALS; ++sp) {
+      if (sp < np) {
+        const float* ps = p.partials + sp * p.partial_stride + (src - p.x);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) pv[sp][k] = *reinterpret_cast<const float4*>(ps + k * 128 + lane * 4);
+      }
+    }
+#pragma unroll
+    for (int sp = 0; sp < LN_MAX_PARTIALS; ++sp) {
+      if (sp < np) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          x[k].x += pv[sp][k].x; x[k].y += pv[sp][k].y; x[k].z += pv[sp][k].z; x[k].w += pv[sp][k].w;
+        }
+      }
     }
   }
   if (add) {
@@ -383,8 +402,12 @@ static __global__ void __launch_bounds__(256) build_bias_kernel(const BiasParams
 // ----------------------------------------------------------------------------------------------
 inline int launch_layernorm(const LnParams& p, int D, cudaStream_t s) {
   const int blocks = (p.total_rows + 7) / 8;
-  if (D == 768) UVLT_LAUNCH(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, s, p);
-  else if (D == 1024) UVLT_LAUNCH(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, s, p);
+  if (p.n_partials > LN_MAX_PARTIALS || p.n_partials < 0) return 1;
+  const bool part = p.n_partials > 0;
+  if (D == 768 && part) UVLT_LAUNCH((layernorm_kernel<6, true>), dim3(blocks), dim3(256), 0, s, p);
+  else if (D == 768) UVLT_LAUNCH((layernorm_kernel<6, false>), dim3(blocks), dim3(256), 0, s, p);
+  else if (D == 1024 && part) UVLT_LAUNCH((layernorm_kernel<8, true>), dim3(blocks), dim3(256), 0, s, p);
+  else if (D == 1024) UVLT_LAUNCH((layernorm_kernel<8, false>), dim3(blocks), dim3(256), 0, s, p);
   else return 1;
   return cudaGetLastError() != cudaSuccess;
 }
