@@ -3,9 +3,11 @@
 
 Every role of one persistent CTA (TMA producer, the two MMA issuers, the two slots' softmax groups) is a Python
 generator that yields the barrier it waits on; mbarriers follow the hardware rule (a parity wait succeeds when the
-barrier's current phase parity differs from the waited parity), TMA loads and MMA commits complete after a random
+barrier's current phase parity differs from the waited parity), the named barriers of the MUFU turns and of the LONE
+merge are two-party barriers with a sync side and an arrive side, TMA loads and MMA commits complete after a random
 delay.  The simulation checks that every item list drains (no deadlock), that no ring stage / Q buffer / TMEM region is
-overwritten before its readers are done, and that every consumer reads the tile it expects.
+overwritten before its readers are done, that every consumer reads the tile it expects, that the two slots are never
+inside their exponentials at the same time, and that slot 0 merges the partial that belongs to its item.
 
     python tools/attn3_protocol_sim.py            # sweep of shapes / grids / seeds
 """
@@ -28,6 +30,23 @@ class MBar:
 
     def test(self, parity):
         return (self.phase & 1) != (parity & 1)
+
+
+class NBar:
+    """Named barrier shared by two parties (all warps of a slot collapsed into one agent): completes a phase when both
+    the bar.sync side and the bar.arrive side have reached it."""
+
+    def __init__(self):
+        self.count, self.phase = 0, 0
+
+    def arrive(self):
+        self.count += 1
+        assert self.count <= 2, "named barrier over-subscribed"
+        if self.count == 2:
+            self.count, self.phase = 0, self.phase + 1
+
+    def test(self, target_phase):
+        return self.phase >= target_phase
 
 
 class Geo:
@@ -67,6 +86,10 @@ class Sim:
         self.s_free = [MBar(1), MBar(1)]   # the 8 warp arrivals collapsed into one agent
         self.p_full = [MBar(1), MBar(1)]
         self.pv_done = [MBar(1), MBar(1)]
+        self.turn = [NBar(), NBar()]      # EXP_TURN + slot: that slot may run its exponentials
+        self.xo_full, self.xo_free = NBar(), NBar()
+        self.exp_owner = None             # slot inside its exponentials (the MUFU token: never both)
+        self.xo = None                    # item whose slot-1 partial sits in the exchange buffer
         self.events = []  # (time, fn) asynchronous completions
         self.now = 0
         # data model: what each buffer currently holds / who still reads it
@@ -188,8 +211,17 @@ class Sim:
                 self.later(done)
                 st["k_pv"] += 1
 
+    def nb_sync(self, bar):
+        """bar.sync: arrive, then wait for the phase this arrival belongs to."""
+        target = bar.phase + 1
+        bar.arrive()
+        yield (bar, target)
+
     def softmax(self, t):
         k = 0
+        first_merge = True
+        if t == 1:
+            self.turn[0].arrive()  # slot 0 goes first
         for idx, ord_, it in self.items():
             ns = it["ns"][t]
             for i in range(ns):
@@ -200,13 +232,36 @@ class Sim:
                 if i > 0:
                     yield (self.pv_done[t], (k - 1) & 1)
                     assert self.O[t] == (idx, i), f"softmax slot {t}: O is {self.O[t]} before block {i}"
+                yield from self.nb_sync(self.turn[t])          # the MUFU turn
+                assert self.exp_owner is None, "both slots inside their exponentials"
+                self.exp_owner = t
+                yield (NBar(), 0)                               # let the other roles run while this slot "computes"
+                self.exp_owner = None
+                self.turn[t ^ 1].arrive()
                 self.P[t] = want
                 self.p_full[t].arrive()
                 k += 1
+            if t == 1:
+                for _ in range(it["ns"][0] - it["ns"][1]):     # turns slot 1 does not use
+                    yield from self.nb_sync(self.turn[1])
+                    self.turn[0].arrive()
             if ns == 0:
                 continue
             yield (self.pv_done[t], (k - 1) & 1)
             assert self.O[t] == (idx, ns), f"epilogue slot {t}: O is {self.O[t]}, wanted {(idx, ns)}"
+            merge = it["lone"] and it["ns"][1] > 0
+            if merge and t == 1:
+                if not first_merge:
+                    yield from self.nb_sync(self.xo_free)
+                first_merge = False
+                assert self.xo is None, "slot 1 overwrote a partial that slot 0 has not read"
+                self.xo = idx
+                self.xo_full.arrive()
+            elif merge:
+                yield from self.nb_sync(self.xo_full)
+                assert self.xo == idx, f"slot 0 merged the partial of item {self.xo} into item {idx}"
+                self.xo = None
+                self.xo_free.arrive()
             self.done_items[t].append(idx)
 
     def run(self):
